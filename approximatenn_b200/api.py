@@ -124,7 +124,7 @@ class Backend:
     """One shared library implementing precomp/query for one element type."""
 
     def __init__(self, path: str, dtype, precomp_sym: str, query_sym: str,
-                 free_save_sym: Optional[str] = None, mode: int = ctypes.RTLD_GLOBAL):
+                 free_save_sym: Optional[str] = None, mode: int = ctypes.RTLD_LOCAL):
         if not os.path.exists(path):
             raise FileNotFoundError(
                 f"{path} is missing: build it first (python -c 'import __graft_entry__ as g; g.build()')")
@@ -199,3 +199,44 @@ class Backend:
                           ctypes.byref(dptr) if want_dists else None)
         return Result(_take(ids, (ys.shape[0], save.k), np.uint64),
                       _take(dptr, (ys.shape[0], save.k), self.dtype) if want_dists else None)
+
+
+# ---- the product libraries ---------------------------------------------------------------
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_SUFFIX = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64"}
+_loaded = {}
+
+
+class StageTimes(ctypes.Structure):
+    _fields_ = [("ms", ctypes.c_float * 7)]
+
+
+STAGE_NAMES = ("upload", "means", "hash", "lists_first_group", "lists_rest", "supercharge",
+               "download")
+
+
+def gpu_backend(dtype) -> Backend:
+    """libann_b200_{f32,f64}.so: precomp_gpu / query_gpu on the current CUDA device.
+
+    There is no fallback: a missing library raises here, a missing GPU makes the C library
+    print an error and exit (the reference's behaviour, gpu_comp.c:15-19)."""
+    dt = np.dtype(dtype)
+    if dt not in _loaded:
+        path = os.path.join(_PKG, f"libann_b200_{_SUFFIX[dt]}.so")
+        b = Backend(path, dt, "precomp_gpu", "query_gpu", "free_save")
+        L = b.lib
+        L.gpu_init.restype = None
+        L.gpu_cleanup.restype = None
+        L.annb_launch_count.argtypes = [ctypes.c_int]
+        L.annb_launch_count.restype = ctypes.c_ulong
+        L.annh_last_times.restype = ctypes.POINTER(StageTimes)
+        L.annh_set_timing.argtypes = [ctypes.c_int]
+        L.annh_set_timing.restype = None
+        _loaded[dt] = b
+    return _loaded[dt]
+
+
+def stage_times(b: Backend) -> dict:
+    t = b.lib.annh_last_times().contents
+    return {name: float(t.ms[i]) for i, name in enumerate(STAGE_NAMES)}

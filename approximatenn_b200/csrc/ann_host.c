@@ -1,0 +1,523 @@
+/* ann_host.c — C host driver of the B200 backend: precomp_gpu / query_gpu and the device
+ * lifecycle hooks, i.e. the symbols the reference's ann.c and test programs bind
+ * (/root/reference/algg.h:5-11, gpu_comp.h:11-13).
+ *
+ * The host does what the reference's host does (alg.c:342-434) and nothing else on the
+ * CPU: derive d_short/d_max, draw the random transforms from libc random() in the
+ * reference's order, sequence the device stages, assemble save_t.  All per-point work
+ * runs in the sm_100a kernels behind include/annb200.h.  There is no CPU fallback: every
+ * CUDA failure prints a message and exits, like the reference's OpenCL glue
+ * (gpu_comp.c:15-19, alggp.c:35-41).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <cuda_runtime_api.h>
+
+#include "ann.h"
+#include "algg.h"
+#include "gpu_comp.h"
+#include "annb200.h"
+#include "ann_host.h"
+
+/* ------------------------------------------------------------------------------------ */
+/* errors, lifecycle                                                                     */
+
+void annh_fatal(const char *fmt, const char *detail) {
+  fprintf(stderr, "approximatenn_b200: ");
+  fprintf(stderr, fmt, detail);
+  fprintf(stderr, "\n");
+  exit(1);
+}
+
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      fprintf(stderr, "approximatenn_b200: %s failed at %s:%d: %s\n", #call, __FILE__,  \
+              __LINE__, cudaGetErrorString(e_));                                        \
+      exit(1);                                                                          \
+    }                                                                                   \
+  } while (0)
+
+typedef struct hook { void (*f)(void); struct hook *next; } hook;
+
+static struct {
+  int ready;
+  int device;
+  cudaStream_t stream;
+  hook *hooks;
+  /* one device arena reused across calls; grown on demand, released by gpu_cleanup()  */
+  char *arena;
+  size_t arena_bytes, arena_used;
+  annh_stage_times last;
+  int timing;
+  cudaEvent_t ev[ANNH_STAGES + 1];
+} G;
+
+void gpu_init(void) {
+  if (G.ready) return;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    annh_fatal("no CUDA device: %s (this library has no CPU fallback)",
+               e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  const char *env = getenv("ANN_B200_DEVICE");
+  int dev = 0;
+  if (env && *env) dev = atoi(env);
+  else CK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= count) annh_fatal("ANN_B200_DEVICE=%s is out of range", env ? env : "?");
+  CK(cudaSetDevice(dev));
+  G.device = dev;
+  CK(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  for (int i = 0; i <= ANNH_STAGES; i++) CK(cudaEventCreate(&G.ev[i]));
+  const char *tm = getenv("ANN_B200_TIMING");
+  G.timing = tm && *tm && *tm != '0';
+  G.ready = 1;
+}
+
+void register_cleanup(void (*f)(void)) {
+  hook *h = malloc(sizeof *h);
+  h->f = f;
+  h->next = G.hooks;
+  G.hooks = h;
+}
+
+void gpu_cleanup(void) {
+  if (!G.ready) return;
+  while (G.hooks) {
+    hook *h = G.hooks;
+    G.hooks = h->next;
+    h->f();
+    free(h);
+  }
+  CK(cudaStreamSynchronize(G.stream));
+  if (G.arena) CK(cudaFree(G.arena));
+  G.arena = NULL;
+  G.arena_bytes = G.arena_used = 0;
+  for (int i = 0; i <= ANNH_STAGES; i++) CK(cudaEventDestroy(G.ev[i]));
+  CK(cudaStreamDestroy(G.stream));
+  G.ready = 0;
+}
+
+void *annh_stream(void) { gpu_init(); return G.stream; }
+const annh_stage_times *annh_last_times(void) { return &G.last; }
+void annh_set_timing(int on) { gpu_init(); G.timing = on; }
+
+/* ------------------------------------------------------------------------------------ */
+/* device arena                                                                          */
+
+static void arena_reserve(size_t bytes) {
+  if (bytes <= G.arena_bytes) { G.arena_used = 0; return; }
+  if (G.arena) {
+    CK(cudaStreamSynchronize(G.stream));
+    CK(cudaFree(G.arena));
+  }
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  if (bytes > free_b) {
+    char msg[128];
+    snprintf(msg, sizeof msg, "%.2f GB needed, %.2f GB free", bytes / 1e9, free_b / 1e9);
+    annh_fatal("device memory: %s", msg);
+  }
+  CK(cudaMalloc((void **)&G.arena, bytes));
+  G.arena_bytes = bytes;
+  G.arena_used = 0;
+}
+
+static size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+static void *arena_take(size_t bytes) {
+  size_t at = G.arena_used;
+  G.arena_used += pad256(bytes);
+  if (G.arena_used > G.arena_bytes) annh_fatal("internal: %s", "device arena overrun");
+  return G.arena + at;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* sizes and transforms                                                                  */
+
+void annh_params(size_t n, size_t k, size_t d, size_t *d_short_o, size_t *d_max_o) {
+  /* alg.c:347-357: the division is in ftype, the logarithm in double                   */
+  size_t d_short = ceil(log2((ftype)n / k));
+  size_t d_max = 1;
+  while (d_max < d) d_max <<= 1;
+  if (d_short > d_max) d_short = d_max;
+  *d_short_o = d_short;
+  *d_max_o = d_max;
+}
+
+static int floor_log2_sz(size_t v) {
+  int r = 0;
+  while (v >>= 1) r++;
+  return r;
+}
+
+static double draw_unit(void) {                        /* rand_pr.c:6-8 */
+  return (double)(unsigned long)random() / ((double)RAND_MAX + 1);
+}
+
+/* rand_pr.c:17-30: `picks` swaps of a Fisher-Yates shuffle over [0,range)                */
+static void draw_subperm(size_t picks, size_t range, size_t *p) {
+  for (size_t i = 0; i < range; i++) p[i] = i;
+  for (size_t i = 0; i < picks; i++) {
+    size_t j = (unsigned long)random() % (range - i) + i;
+    size_t t = p[i]; p[i] = p[j]; p[j] = t;
+  }
+}
+
+/* One transform: sweeps are stored "before" first, then "after"; (ci,cj,angle) per plane */
+typedef struct {
+  size_t *ci, *cj;
+  ftype *ang;
+  size_t *perm_b, *perm_ai;
+} host_transform;
+
+static void draw_sweeps(size_t sweeps, size_t planes, size_t range, size_t *ci, size_t *cj,
+                        ftype *ang, size_t *tmp) {
+  for (size_t s = 0; s < sweeps; s++) {               /* rand_pr.c:10-16 */
+    draw_subperm(2 * planes, range, tmp);
+    for (size_t q = 0; q < planes; q++) {
+      ci[s * planes + q] = tmp[2 * q];
+      cj[s * planes + q] = tmp[2 * q + 1];
+      ang[s * planes + q] = draw_unit() * M_PI;
+    }
+  }
+}
+
+static void draw_transform(host_transform *t, size_t rots_b, size_t len_b, size_t rots_a,
+                           size_t len_a, size_t d_short, size_t d, size_t d_max) {
+  size_t pb = rots_b * len_b, pa = rots_a * len_a;
+  t->ci = malloc(sizeof(size_t) * (pb + pa + 1));
+  t->cj = malloc(sizeof(size_t) * (pb + pa + 1));
+  t->ang = malloc(sizeof(ftype) * (pb + pa + 1));
+  t->perm_b = malloc(sizeof(size_t) * d_max);
+  t->perm_ai = malloc(sizeof(size_t) * d_max);
+  size_t *tmp = malloc(sizeof(size_t) * d_max);
+  draw_sweeps(rots_b, len_b, d, t->ci, t->cj, t->ang, tmp);                    /* alg.c:65 */
+  draw_sweeps(rots_a, len_a, d_short, t->ci + pb, t->cj + pb, t->ang + pb, tmp); /* alg.c:66 */
+  draw_subperm(d, d_max, t->perm_b);                                           /* alg.c:67 */
+  draw_subperm(d_short, d_max, t->perm_ai);                                    /* alg.c:70 */
+  free(tmp);
+}
+
+static void free_transform(host_transform *t) {
+  free(t->ci); free(t->cj); free(t->ang); free(t->perm_b); free(t->perm_ai);
+}
+
+/* ---- the d_short x d projection matrix of one transform (save->bases), alg.c:189-217 ----
+ * Tiny (d_short rows of d_max values), so it is evaluated on the host with the reference's
+ * exact operation order: identity -> perm_ai embed -> reversed "after" sweeps with the
+ * plane coordinates swapped -> Walsh-Hadamard -> perm_b projection -> reversed "before"
+ * sweeps.  Compiled with -ffp-contract=off.                                              */
+static void host_sweep(ftype *v, size_t planes, const size_t *ci, const size_t *cj,
+                       const ftype *ang) {
+  for (size_t q = 0; q < planes; q++) {
+    ftype c = cos(ang[q]), s = sin(ang[q]);
+    ftype a = v[ci[q]], b = v[cj[q]];
+    ftype na = a * c - b * s, nb = a * s + b * c;
+    v[ci[q]] = na;
+    v[cj[q]] = nb;
+  }
+}
+
+static void host_walsh(ftype *z, size_t len) {
+  int levels = floor_log2_sz(len);
+  for (int lev = 0; lev < levels; lev++) {
+    size_t stride = (size_t)1 << lev;
+    ftype div = lev % 2 + 1;
+    for (size_t base = 0; base < len; base += 2 * stride)
+      for (size_t o = 0; o < stride; o++) {
+        ftype a = z[base + o], b = z[base + o + stride];
+        z[base + o] = (a + b) / div;
+        z[base + o + stride] = (a - b) / div;
+      }
+    if (lev == 0 && levels % 2) {
+      ftype r = 1 / sqrt(2.0);
+      for (size_t i = 0; i < len; i++) z[i] *= r;
+    }
+  }
+}
+
+static void projection_rows(const host_transform *t, size_t rots_b, size_t len_b, size_t rots_a,
+                            size_t len_a, size_t d_short, size_t d, size_t d_max, ftype *out) {
+  size_t pb = rots_b * len_b;
+  ftype *z = malloc(sizeof(ftype) * d_max);
+  for (size_t r = 0; r < d_short; r++) {
+    for (size_t y = 0; y < d_max; y++) z[y] = (t->perm_ai[y] == r) ? 1 : 0;
+    for (size_t s = rots_a; s-- > 0;)
+      host_sweep(z, len_a, t->cj + pb + s * len_a, t->ci + pb + s * len_a, t->ang + pb + s * len_a);
+    host_walsh(z, d_max);
+    ftype *o = out + r * d;
+    for (size_t y = 0; y < d_max; y++)
+      if (t->perm_b[y] < d) o[t->perm_b[y]] = z[y];
+    for (size_t s = rots_b; s-- > 0;)
+      host_sweep(o, len_b, t->cj + s * len_b, t->ci + s * len_b, t->ang + s * len_b);
+  }
+  free(z);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* stage timing (CUDA events on the library stream; off unless asked for)                */
+
+static void mark(int i) { if (G.timing) CK(cudaEventRecord(G.ev[i], G.stream)); }
+
+static void collect_times(void) {
+  if (!G.timing) return;
+  for (int i = 0; i < ANNH_STAGES; i++) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, G.ev[i], G.ev[i + 1]));
+    G.last.ms[i] = ms;
+  }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* precomp_gpu                                                                            */
+
+static void validate(size_t n, size_t k, size_t d, int tries, size_t len_b, size_t len_a,
+                     size_t d_short) {
+  if (n < 2 || k < 1 || d < 1 || tries < 1) annh_fatal("%s", "n >= 2, k >= 1, d >= 1, tries >= 1 required");
+  if (n >= 0xFFFFFFFFull) annh_fatal("%s", "n must be below 2^32 - 1 (32-bit ids on the device)");
+  if (k >= n) annh_fatal("%s", "k must be smaller than n");
+  if (k > 256) annh_fatal("%s", "k > 256 is not supported");
+  if (d_short > 28) annh_fatal("%s", "more than 2^28 buckets per try");
+  if (2 * len_b > d) annh_fatal("%s", "2*rot_len_before must not exceed d (rand_pr.c:17-30)");
+  if (2 * len_a > d_short) annh_fatal("%s", "2*rot_len_after must not exceed d_short (alg.c:66)");
+}
+
+size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries,
+                    size_t rots_before, size_t rot_len_before, size_t rots_after,
+                    size_t rot_len_after, save_t *save, ftype **dists_o) {
+  gpu_init();
+  CK(cudaSetDevice(G.device));
+  size_t d_short, d_max;
+  annh_params(n, k, d, &d_short, &d_max);
+  validate(n, k, d, tries, rot_len_before, rot_len_after, d_short);
+  const size_t T = (size_t)tries, buckets = (size_t)1 << d_short;
+  const size_t planes = rots_before * rot_len_before + rots_after * rot_len_after;
+  cudaStream_t st = G.stream;
+
+  /* 1. transforms: ALL tries are drawn before any compute (alg.c:388-392)              */
+  host_transform *tf = malloc(sizeof(host_transform) * T);
+  for (size_t t = 0; t < T; t++)
+    draw_transform(tf + t, rots_before, rot_len_before, rots_after, rot_len_after, d_short, d, d_max);
+  annb_u32 *h_idx = malloc(sizeof(annb_u32) * (T * planes * 2 + 1));
+  ftype *h_cs = malloc(sizeof(ftype) * (T * planes * 2 + 1));
+  annb_u32 *h_permb = malloc(sizeof(annb_u32) * T * d_max);
+  annb_u32 *h_pick = malloc(sizeof(annb_u32) * (T * d_short + 1));
+  for (size_t t = 0; t < T; t++) {
+    for (size_t q = 0; q < planes; q++) {
+      h_idx[(t * planes + q) * 2] = (annb_u32)tf[t].ci[q];
+      h_idx[(t * planes + q) * 2 + 1] = (annb_u32)tf[t].cj[q];
+      /* libm in double on the ftype-rounded angle, then rounded to ftype (ocl2c.h:10)  */
+      h_cs[(t * planes + q) * 2] = cos(tf[t].ang[q]);
+      h_cs[(t * planes + q) * 2 + 1] = sin(tf[t].ang[q]);
+    }
+    for (size_t y = 0; y < d_max; y++) {
+      h_permb[t * d_max + y] = (annb_u32)tf[t].perm_b[y];
+      if (tf[t].perm_ai[y] < d_short) h_pick[t * d_short + tf[t].perm_ai[y]] = (annb_u32)y;
+    }
+  }
+
+  /* 2. device memory plan                                                              */
+  annb_transform_desc desc;
+  memset(&desc, 0, sizeof desc);
+  desc.n = n; desc.d = d; desc.d_max = d_max; desc.d_short = d_short;
+  desc.rots_before = rots_before; desc.rot_len_before = rot_len_before;
+  desc.rots_after = rots_after; desc.rot_len_after = rot_len_after;
+  desc.tries = tries;
+  desc.inv_sqrt2 = 1 / sqrt(2.0);
+  const size_t w = sizeof(ftype);
+  const size_t list_bytes = n * k * (4 + w);                   /* one per-try list      */
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  free_b += G.arena_bytes;
+  size_t fixed = pad256(n * d * w) * 2 + pad256(d * w) + pad256(T * n * 4) +
+                 pad256(buckets * 4) + pad256((buckets + 1) * 4) + pad256(n * 4) * 2 +
+                 pad256(T * 4) + pad256(annb_scan_tmp_bytes(buckets)) +
+                 pad256(T * planes * 2 * 4 + 4) + pad256(T * planes * 2 * w + w) +
+                 pad256(T * d_max * 4) + pad256(T * d_short * 4 + 4) +
+                 pad256(annb_hash_scratch_bytes(&desc)) +
+                 pad256(n * k * 4) * 2 + pad256(n * k * w) * 3 + pad256(n * k * sizeof(size_t)) + 4096;
+  size_t group = T;                                            /* lists kept before a merge */
+  while (group > 1 && fixed + group * list_bytes + 512 > free_b * 9 / 10) group--;
+  if ((size_t)k * T < 16) group = T;
+  arena_reserve(fixed + group * list_bytes + 512);
+
+  ftype *dX = arena_take(n * d * w), *dXs = arena_take(n * d * w), *dmean = arena_take(d * w);
+  annb_u32 *dhash = arena_take(T * n * 4);
+  annb_u32 *dcount = arena_take(buckets * 4), *doffset = arena_take((buckets + 1) * 4);
+  annb_u32 *dorder_tmp = arena_take(n * 4), *dorder = arena_take(n * 4);
+  annb_u32 *dtmax = arena_take(T * 4);
+  void *dscan = arena_take(annb_scan_tmp_bytes(buckets));
+  annb_u32 *d_idx = arena_take(T * planes * 2 * 4 + 4);
+  ftype *d_cs = arena_take(T * planes * 2 * w + w);
+  annb_u32 *d_permb = arena_take(T * d_max * 4), *d_pick = arena_take(T * d_short * 4 + 4);
+  void *dhscratch = arena_take(annb_hash_scratch_bytes(&desc));
+  annb_u32 *dl_ids = arena_take(group * n * k * 4);
+  ftype *dl_dist = arena_take(group * n * k * w);
+  annb_u32 *dm_ids = arena_take(n * k * 4), *dm_ids2 = arena_take(n * k * 4);
+  ftype *dm_dist = arena_take(n * k * w), *dm_dist2 = arena_take(n * k * w);
+  size_t *dout_ids = arena_take(n * k * sizeof(size_t));
+  ftype *dout_dist = arena_take(n * k * w);
+
+  /* 3. upload                                                                          */
+  mark(0);
+  CK(cudaMemcpyAsync(dX, points, n * d * w, cudaMemcpyHostToDevice, st));
+  if (planes) {
+    CK(cudaMemcpyAsync(d_idx, h_idx, T * planes * 2 * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_cs, h_cs, T * planes * 2 * w, cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemcpyAsync(d_permb, h_permb, T * d_max * 4, cudaMemcpyHostToDevice, st));
+  if (d_short) CK(cudaMemcpyAsync(d_pick, h_pick, T * d_short * 4, cudaMemcpyHostToDevice, st));
+  desc.plane_idx = d_idx; desc.plane_cs = d_cs; desc.perm_b = d_permb; desc.pick = d_pick;
+
+  /* 4. S0 column means (alg.c:367-368); the accumulator borrows the sorted-copy buffer */
+  mark(1);
+  annb_fold_rows(dX, dXs, n, d, 1, st);
+  for (size_t len = n >> 1; len >> 1; len >>= 1) annb_fold_rows(dXs, dXs, len, d, 0, st);
+  annb_scale_means(dXs, n, d, dmean, st);
+
+  /* 5. S1 hashes of every try in one pass over the points                              */
+  mark(2);
+  annb_hash_points(dX, dmean, &desc, dhash, dhscratch, st);
+  mark(3);
+
+  if (save) {
+    save->tries = tries; save->n = n; save->k = k; save->d_short = d_short; save->d_long = d;
+    save->row_means = malloc(w * d);
+    save->which_par = malloc(sizeof(size_t *) * T);
+    save->par_maxes = malloc(sizeof(size_t) * T);
+    save->bases = malloc(w * T * d_short * d);
+    CK(cudaMemcpyAsync(save->row_means, dmean, d * w, cudaMemcpyDeviceToHost, st));
+    for (size_t t = 0; t < T; t++)
+      projection_rows(tf + t, rots_before, rot_len_before, rots_after, rot_len_after, d_short, d,
+                      d_max, save->bases + t * d_short * d);
+  }
+
+  /* 6. per try: S2 bucket tables, S3 k best; merge whenever `group` lists are waiting    */
+  const size_t row_len = k * T;
+  const int tiny_merge = row_len < 16;
+  const size_t prefix = tiny_merge ? row_len : (size_t)1 << floor_log2_sz(row_len);
+  int have_merged = 0;
+  size_t *dtable = NULL;
+  size_t dtable_cap = 0;
+  int admit[64];
+  for (size_t t0 = 0; t0 < T; t0 += group) {
+    size_t g = T - t0 < group ? T - t0 : group;
+    if (g > 64) annh_fatal("%s", "more than 64 tries per merge group");
+    for (size_t j = 0; j < g; j++) {
+      size_t t = t0 + j;
+      annb_build_buckets(dhash + t * n, n, buckets, dcount, doffset, dorder_tmp, dorder,
+                         dtmax + t, dscan, st);
+      if (save) {                                  /* padded table for save->which_par[t] */
+        annb_u32 tm = 0;
+        CK(cudaMemcpyAsync(&tm, dtmax + t, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        size_t cells = buckets * (size_t)tm;
+        if (cells > dtable_cap) {
+          if (dtable) CK(cudaFree(dtable));
+          CK(cudaMalloc((void **)&dtable, (cells ? cells : 1) * sizeof(size_t)));
+          dtable_cap = cells;
+        }
+        annb_export_table(doffset, dorder, n, buckets, tm, dtable, st);
+        save->par_maxes[t] = tm;
+        save->which_par[t] = malloc((cells ? cells : 1) * sizeof(size_t));
+        CK(cudaMemcpyAsync(save->which_par[t], dtable, cells * sizeof(size_t), cudaMemcpyDeviceToHost, st));
+      }
+      annb_gather_rows(dX, dorder, n, d, dXs, st);
+      annb_leaf_topk(dXs, dorder, doffset, dhash + t * n, dtmax + t, n, d, d_short, k,
+                     dl_ids + j * n * k, dl_dist + j * n * k, st);
+      size_t first = k * t;
+      admit[j] = first >= prefix ? 0 : (int)(prefix - first < k ? prefix - first : k);
+    }
+    if (tiny_merge) {
+      annb_merge_lists_tiny(dl_ids, dl_dist, (int)g, n, k, dm_ids, dm_dist, st);
+    } else {
+      int corner_list = -1, corner_pos = 0;
+      if (prefix < row_len && group == T) {        /* DESIGN.md "prefix corner"          */
+        corner_list = (int)(prefix / k);
+        corner_pos = (int)(prefix % k);
+      }
+      annb_merge_lists(dl_ids, dl_dist, (int)g, admit, corner_list, corner_pos,
+                       have_merged ? dm_ids : NULL, have_merged ? dm_dist : NULL, n, k,
+                       dm_ids2, dm_dist2, st);
+      annb_u32 *ti = dm_ids; dm_ids = dm_ids2; dm_ids2 = ti;
+      ftype *td = dm_dist; dm_dist = dm_dist2; dm_dist2 = td;
+    }
+    have_merged = 1;
+    if (t0 == 0) mark(4);
+  }
+  if (dtable) { CK(cudaStreamSynchronize(st)); CK(cudaFree(dtable)); }
+  mark(5);
+
+  /* 7. S5 supercharging (alg.c:313-327); the graph is the merged lists themselves        */
+  if (k * (k + 1) < 16)
+    annb_supercharge_tiny(dX, dX, dm_ids, dm_dist, dm_ids, n, d, k, 0, n, 1, dout_ids,
+                          dists_o ? dout_dist : NULL, st);
+  else
+    annb_supercharge(dX, dX, dm_ids, dm_dist, dm_ids, n, d, k, 0, n, 1, dout_ids,
+                     dists_o ? dout_dist : NULL, st);
+  mark(6);
+
+  /* 8. results                                                                          */
+  size_t *result = malloc(sizeof(size_t) * n * k);
+  CK(cudaMemcpyAsync(result, dout_ids, sizeof(size_t) * n * k, cudaMemcpyDeviceToHost, st));
+  if (dists_o) {
+    *dists_o = malloc(w * n * k);
+    CK(cudaMemcpyAsync(*dists_o, dout_dist, w * n * k, cudaMemcpyDeviceToHost, st));
+  }
+  annb_u32 *h_tmax = malloc(4 * T);
+  CK(cudaMemcpyAsync(h_tmax, dtmax, 4 * T, cudaMemcpyDeviceToHost, st));
+  mark(7);
+  CK(cudaStreamSynchronize(st));
+  collect_times();
+  for (size_t t = 0; t < T; t++)
+    if ((d_short + 1) * (size_t)h_tmax[t] < 16)
+      annh_fatal("%s", "candidate rows shorter than 16 slots (n far too small for this k)");
+  free(h_tmax);
+
+  if (save) {                                                   /* alg.c:428-432 */
+    save->graph = result;
+    result = malloc(sizeof(size_t) * n * k);
+    memcpy(result, save->graph, sizeof(size_t) * n * k);
+  }
+  for (size_t t = 0; t < T; t++) free_transform(tf + t);
+  free(tf); free(h_idx); free(h_cs); free(h_permb); free(h_pick);
+  return result;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* query_gpu — see ann_query.c                                                            */
+
+/* ------------------------------------------------------------------------------------ */
+/* ann.h front door.  Weak, so that the reference's own ann.c wins when it is linked in.  */
+
+__attribute__((weak)) void free_save(save_t *save) {            /* ann.c:25-34 */
+  annh_forget_save(save);
+  for (int i = 0; i < save->tries; i++) free(save->which_par[i]);
+  free(save->which_par);
+  free(save->par_maxes);
+  free(save->graph);
+  free(save->row_means);
+  free(save->bases);
+}
+
+__attribute__((weak)) size_t *precomp(size_t n, size_t k, size_t d, const ftype *points, int tries,
+                                      size_t rots_before, size_t rot_len_before, size_t rots_after,
+                                      size_t rot_len_after, save_t *save, ftype **dists,
+                                      char use_cpu) {
+  if (use_cpu)
+    annh_fatal("%s", "use_cpu != 0: this library contains no CPU path (link the reference's algc.c and ann.c for one)");
+  return precomp_gpu(n, k, d, points, tries, rots_before, rot_len_before, rots_after,
+                     rot_len_after, save, dists);
+}
+
+__attribute__((weak)) size_t *query(const save_t *save, const ftype *points, size_t ycnt,
+                                    const ftype *y, ftype **dists, char use_cpu) {
+  if (use_cpu)
+    annh_fatal("%s", "use_cpu != 0: this library contains no CPU path (link the reference's algc.c and ann.c for one)");
+  return query_gpu(save, points, ycnt, y, dists);
+}

@@ -1,0 +1,36 @@
+/* ann_host.h — internals shared by the C host files (not part of the public API). */
+#ifndef ANN_HOST_H
+#define ANN_HOST_H
+#include <stddef.h>
+#include "ann.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* prints "approximatenn_b200: <fmt % detail>" to stderr and exits(1): the reference's error
+ * behaviour (gpu_comp.c:15-19), the API has no error channel                              */
+void annh_fatal(const char *fmt, const char *detail);
+
+/* d_short / d_max of a problem (alg.c:347-357) */
+void annh_params(size_t n, size_t k, size_t d, size_t *d_short, size_t *d_max);
+
+/* the library's CUDA stream (cudaStream_t), after gpu_init() */
+void *annh_stream(void);
+
+/* Device-time of the stages of the last precomp_gpu call, measured with CUDA events on
+ * the library stream when timing is on (annh_set_timing(1) or ANN_B200_TIMING=1).
+ *   0 upload  1 means  2 hash  3 buckets+leaf lists (first merge group)  4 remaining groups
+ *   5 supercharge  6 download                                                            */
+#define ANNH_STAGES 7
+typedef struct { float ms[ANNH_STAGES]; } annh_stage_times;
+const annh_stage_times *annh_last_times(void);
+void annh_set_timing(int on);
+
+/* drops any device-resident copy of `save` kept for query_gpu (called by free_save)      */
+void annh_forget_save(const save_t *save);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

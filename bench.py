@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""bench.py — all-points kNN throughput of the B200 backend on BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg3]
+
+One "step" = one full precomp (centre, hash, bucket tables, per-try lists, merge,
+supercharge) over one batch of synthetic Gaussian points.  Workload at N=1 is BASELINE
+config 3: n=1,000,000 d=64 k=16 float, 8 tries + supercharge, reference default rotations.
+
+Printed JSON (one line, rank 0):
+  value     points/s, device time only: inputs resident in HBM when the timed region starts
+            (CUDA events on the library's stream, from after the upload to before the download)
+  e2e       points/s through the reference-facing C-ABI call precomp_gpu(host pointers):
+            pinned host input -> H2D -> all stages -> D2H into the malloc()ed result arrays
+  roofline  the dominant kernel against the measured peak (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU restatement of the reference (oracle/, pinned bit-exact to the
+            reference's C path) timed on this box's host, 1 core, on a bounded sample
+`--impl reference` times that CPU path alone and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (n, d, k, tries, dtype)
+    "cfg1": (16384, 16, 10, 10, np.float32),
+    "cfg2": (65536, 32, 16, 8, np.float64),
+    "cfg3": (1_000_000, 64, 16, 8, np.float32),
+    "cfg4": (10_000_000, 64, 16, 8, np.float32),
+}
+ROT = (6, 1, 1, 1)          # reference defaults (time_results.c:16-17)
+METRIC = "all-points kNN points/sec (precomp: hash + per-try lists + merge + supercharge)"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return float(j["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def synth_points(n, d, dtype, seed=1):
+    rng = np.random.default_rng(seed)
+    out = np.empty((n, d), dtype=dtype)
+    step = 1 << 18
+    for i in range(0, n, step):
+        out[i:i + step] = rng.standard_normal((min(step, n - i), d), dtype=np.float32).astype(dtype)
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.idx, self.stop_flag, self.rows = gpu_index, threading.Event(), []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4)
+                          if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_baseline(cfg, pts, sample_points):
+    """Reference algorithm on the host (1 core): bounded sample at full problem size."""
+    import oracle
+    n, d, k, tries, dtype = cfg
+    orc = oracle.restatement(dtype)
+    rng = np.random.default_rng(99)
+    sample = rng.choice(n, size=min(sample_points, n), replace=False)
+    from approximatenn_b200.api import srandom
+    srandom(4242)
+    t0 = time.time()
+    c = oracle.sampled_cost(orc, pts, k, tries, sample, *ROT)
+    per_point = c["prepare_s"] / n + c["row_s"] + c["supercharge_s"]
+    return {"value": 1.0 / per_point, "unit": "points/s", "cores": 1, "kind": "port",
+            "sample": (f"oracle/ann_oracle.c (bit-exact restatement of the reference's precomp_cpu; the "
+                       f"reference itself needs n*L*d*4 B = >100 GB of scratch at this size): hashing+tables "
+                       f"for all {n} points, then per-try rows+merge for {c['rows']} points and supercharge "
+                       f"for {len(sample)} sampled points; {time.time() - t0:.1f} s of CPU; points/s = "
+                       f"1/(prepare/n + row + supercharge)"),
+            "detail": {k_: float(v) for k_, v in c.items()}}
+
+
+def run_reference_arm(args, cfg, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, d, k, tries, dtype = cfg
+    pts = synth_points(n, d, dtype)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(cfg, pts, args.cpu_sample)
+        if i >= args.warmup:
+            vals.append(cb)
+    v = statistics.mean(c["value"] for c in vals)
+    cb = vals[-1]
+    cb["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "points/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * n / v, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32" if dtype == np.float32 else "f64",
+            "data": "synthetic", "config": workload_config(cfg, name, args.gpus),
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, name, gpus):
+    n, d, k, tries, dtype = cfg
+    return {"workload": f"BASELINE {name}: n={n} d={d} k={k} {np.dtype(dtype).name}, {tries} tries + supercharge, "
+                        f"rotations {ROT}, iid N(0,1) points",
+            "n": n, "d": d, "k": k, "tries": tries, "gpus": gpus,
+            "l2": "inputs (n*d*4 B = %.0f MB) exceed the 126 MB L2; no flush needed" % (n * d * np.dtype(dtype).itemsize / 1e6)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--cpu-sample", type=int, default=256, help="points in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    n, d, k, tries, dtype = cfg
+
+    if args.impl == "reference":
+        run_reference_arm(args, cfg, args.config)
+        return
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    os.environ.setdefault("ANN_B200_DEVICE", str(local))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from approximatenn_b200.api import gpu_backend, srandom, stage_times, _libc
+    gpu = gpu_backend(dtype)
+    gpu.lib.gpu_init()
+    gpu.lib.annh_set_timing(1)
+
+    # pinned host input: the buffer the caller hands to precomp_gpu
+    host = torch.empty((n, d), dtype=torch.float32 if dtype == np.float32 else torch.float64,
+                       pin_memory=True)
+    pts = host.numpy()
+    pts[:] = synth_points(n, d, dtype)
+
+    def step():
+        dptr = ctypes.c_void_p()
+        srandom(1001)
+        ids = gpu.precomp_raw(n, k, d, pts.ctypes.data, tries, *ROT, None, ctypes.byref(dptr))
+        st = stage_times(gpu)
+        _libc.free(ids)
+        _libc.free(dptr)
+        return st
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    gpu.lib.annb_launch_count(1)
+    barrier()
+    t0 = time.perf_counter()
+    stages = [step() for _ in range(args.steps)]
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = int(gpu.lib.annb_launch_count(0))
+    sampler.stop_flag.set()
+    sampler.join()
+
+    dev_keys = ("means", "hash", "lists_first_group", "lists_rest", "supercharge")
+    dev_ms = [sum(s[k_] for k_ in dev_keys) for s in stages]
+    dev_total_s = sum(dev_ms) / 1e3
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([dev_total_s, wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_total_s, wall = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+
+    w = np.dtype(dtype).itemsize
+    mean_stage = {k_: statistics.mean(s[k_] for s in stages) for k_ in stages[0]}
+    peak, peak_src = measured_peaks()
+    # dominant HBM-bound kernel: supercharge.  Algorithmic bytes per launch:
+    # n*(P2-k) gathered rows of (4 + d*w) B, + own lists in, + size_t ids and dists out.
+    P2 = 1 << ((k * (k + 1)).bit_length() - 1)
+    sc_bytes = n * (P2 - k) * (4 + d * w) + n * k * (4 + w) + n * k * (8 + w)
+    sc_s = mean_stage["supercharge"] / 1e3
+    roofline = {"kernel": "supercharge_kernel", "bound": "hbm", "achieved": sc_bytes / sc_s / 1e9,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": sc_bytes / sc_s / 1e9 / peak, "traffic": None,
+                "share_of_device_time": mean_stage["supercharge"] / statistics.mean(dev_ms)}
+    line = {"metric": METRIC, "value": n * args.steps / dev_total_s, "unit": "points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_total_s / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if dtype == np.float32 else "f64", "data": "synthetic",
+            "config": workload_config(cfg, args.config, world),
+            "e2e": {"value": n * args.steps / wall, "unit": "points/s",
+                    "h2d_bytes_per_step": n * d * w, "d2h_bytes_per_step": n * k * (8 + w),
+                    "ms_per_step": 1e3 * wall / args.steps},
+            "gpu_launches": launches, "stage_ms": mean_stage, "roofline": roofline,
+            "clocks": sampler.summary()}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(cfg, pts, args.cpu_sample)
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,132 @@
+/* annb200.h — the thin C-ABI between the C host driver (approximatenn_b200/csrc/ann_host.c)
+ * and the sm_100a kernels (approximatenn_b200/csrc/annb_kernels.cu).
+ *
+ * Every function enqueues work on `stream` and returns; all pointers are DEVICE pointers
+ * unless named host_*.  One library is built per element type (ftype.h), so `ftype` below
+ * is float in libann_b200_f32.so and double in libann_b200_f64.so.  Ids are 32-bit on the
+ * device (n < 2^32 - 1); the sentinel "no point" is n, as in the reference.
+ *
+ * Each entry cites the part of the reference it replaces (paths under /root/reference).
+ * The reference launches one OpenCL kernel per arrow of its dataflow through global
+ * memory; the stages here are fused differently, but each
+ * produces bit-identical values to the reference's pure-C path.
+ */
+#ifndef ANNB200_H
+#define ANNB200_H
+#include <stddef.h>
+#include "ftype.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef unsigned int annb_u32;
+typedef struct CUstream_st *annb_stream;      /* == cudaStream_t */
+
+/* ---- S0: column means --------------------------------------------------------------
+ * One level of the reference's stride-halving row sum (alg.c:122-128;
+ * compute.cl:15-31): dst[x][c] = src[x][c] + src[x+len/2][c] (+ src[len-1][c] for x == 0 when
+ * len is odd), x < len/2, with the reference's association order for the first level
+ * (first != 0) and for the in-place levels (first == 0).  dst may alias src when first == 0. */
+void annb_fold_rows(const ftype *src, ftype *dst, size_t len, size_t d, int first,
+                    annb_stream stream);
+/* mean[c] = acc[c] / n   (compute.cl:36-39) */
+void annb_scale_means(const ftype *acc, size_t n, size_t d, ftype *mean, annb_stream stream);
+
+/* ---- S1: centre + random orthogonal transform + sign hash ---------------------------
+ * Replaces subtract_off, apply_rotation, apply_permutation, apply_walsh_step,
+ * apply_perm_inv, compute_signs (compute.cl:44-122,223-231; driver alg.c:154-183) for
+ * `tries` transforms in one pass over the points.  Per try t the host supplies
+ *   plane_idx[t][sweep][plane][2]   coordinates of each Givens plane (before sweeps first,
+ *                                   then after sweeps), plane_cs the matching (cos, sin)
+ *   perm_b[t][d_max]                sub-permutation embedding d -> d_max
+ *   pick[t][d_short]                transformed coordinate that feeds hash bit i (MSB first)
+ * hash[t][p] receives the d_short-bit bucket id of point p.                              */
+typedef struct {
+  size_t n, d, d_max, d_short;
+  size_t rots_before, rot_len_before, rots_after, rot_len_after;
+  int tries;
+  ftype inv_sqrt2;                 /* (ftype)(1/sqrt(2.0)), computed on the host           */
+  const annb_u32 *plane_idx;
+  const ftype *plane_cs;
+  const annb_u32 *perm_b;
+  const annb_u32 *pick;
+} annb_transform_desc;
+/* scratch: device workspace of annb_hash_scratch_bytes() bytes (may be NULL when 0)     */
+size_t annb_hash_scratch_bytes(const annb_transform_desc *t);
+void annb_hash_points(const ftype *points, const ftype *mean, const annb_transform_desc *t,
+                      annb_u32 *hash, void *scratch, annb_stream stream);
+
+/* ---- S2: bucket tables (replaces the serial host loop alg.c:252-267) ------------------
+ * count[b]   = points hashing to b            (count has `buckets` entries, zeroed here)
+ * offset[b]  = exclusive prefix sum, offset[buckets] = n
+ * order[..]  = point ids grouped by bucket, DEcreasing id inside a bucket (the reference's
+ *              table rows, without the padding)
+ * *tmax      = largest bucket (the reference's par_maxes[t])
+ * sorted_points[r][:] = points[order[r]][:]   (bucket-contiguous copy for S3)
+ * scan_tmp needs annb_scan_tmp_bytes(buckets) bytes.                                      */
+size_t annb_scan_tmp_bytes(size_t buckets);
+void annb_build_buckets(const annb_u32 *hash, size_t n, size_t buckets,
+                        annb_u32 *count, annb_u32 *offset, annb_u32 *order_tmp,
+                        annb_u32 *order, annb_u32 *tmax, void *scan_tmp, annb_stream stream);
+void annb_gather_rows(const ftype *points, const annb_u32 *order, size_t n, size_t d,
+                      ftype *sorted_points, annb_stream stream);
+/* padded table as save_t stores it (which_par[t], [buckets][tmax] size_t, pad = n)       */
+void annb_export_table(const annb_u32 *offset, const annb_u32 *order, size_t n, size_t buckets,
+                       size_t tmax, size_t *table, annb_stream stream);
+
+/* ---- S3: candidate distances + per-point k best of one try ----------------------------
+ * Replaces compute_which, compute_diffs_squared, add_cols_step, sort_two_step, rdups for
+ * the per-try rows (compute.cl:135-217,238-246; alg.c:274-288).  A point's candidates
+ * are the slots p < P of the virtual row [bucket h, h^1, h^2, h^4, ...] (tmax slots each),
+ * P = 2^floor(log2((d_short+1)*tmax)) — the reference's prefix rule (SURVEY §8.A.3 rule 5).
+ * list_ids/list_dist: [n][k], ascending squared distance, (n, +inf) where fewer than k
+ * finite candidates exist.  `tmax` is read on the device.                                 */
+void annb_leaf_topk(const ftype *sorted_points, const annb_u32 *order, const annb_u32 *offset,
+                    const annb_u32 *hash, const annb_u32 *tmax, size_t n, size_t d,
+                    size_t d_short, size_t k, annb_u32 *list_ids, ftype *list_dist,
+                    annb_stream stream);
+
+/* ---- S4: merge of the per-try lists (first sort_and_uniq of det_results, alg.c:312) ----
+ * lists: [n_lists][n][k]; admit[i] = number of leading entries of list i that fall inside
+ * the sorted prefix (k, or fewer for the try that straddles 2^floor(log2(k*tries))).
+ * corner_list/corner_pos: the list entry sitting in the first slot OUTSIDE the prefix
+ * (or corner_list < 0 when the row length is a power of two) — see DESIGN.md "prefix
+ * corner".  merged: [n][k].  If merged_in != NULL it is treated as one more, fully
+ * admitted list (running merge).                                                          */
+void annb_merge_lists(const annb_u32 *lists_ids, const ftype *lists_dist, int n_lists,
+                      const int *host_admit, int corner_list, int corner_pos,
+                      const annb_u32 *merged_in_ids, const ftype *merged_in_dist,
+                      size_t n, size_t k, annb_u32 *merged_ids, ftype *merged_dist,
+                      annb_stream stream);
+
+/* ---- S5: supercharging (supercharge + compdists + second sort_and_uniq, alg.c:313-335) --
+ * For each query row x in [row_begin, row_end): candidates = own list ++ the lists of its
+ * neighbours (graph rows), prefix 2^floor(log2(k(k+1))); distances from queries[x] to
+ * points[id]; out rows are relative to row_begin.  exclude_self: the reference excludes
+ * id == x only when the query set IS the point set (compute.cl:145).
+ * graph may be the merged ids themselves (precomp) or save->graph (query).                */
+void annb_supercharge(const ftype *queries, const ftype *points, const annb_u32 *own_ids,
+                      const ftype *own_dist, const annb_u32 *graph, size_t n, size_t d,
+                      size_t k, size_t row_begin, size_t row_end, int exclude_self,
+                      size_t *out_ids, ftype *out_dist, annb_stream stream);
+
+/* ---- literal fall-back for rows shorter than 16 slots ---------------------------------
+ * The reference's sort degenerates to independent blocks when a row has fewer than 16
+ * slots (k*tries < 16 or k(k+1) < 16; SURVEY §8.A.3 rule 5).  These two emulate the
+ * network literally, one thread per row.                                                  */
+void annb_merge_lists_tiny(const annb_u32 *lists_ids, const ftype *lists_dist, int n_lists,
+                           size_t n, size_t k, annb_u32 *merged_ids, ftype *merged_dist,
+                           annb_stream stream);
+void annb_supercharge_tiny(const ftype *queries, const ftype *points, const annb_u32 *own_ids,
+                           const ftype *own_dist, const annb_u32 *graph, size_t n, size_t d,
+                           size_t k, size_t row_begin, size_t row_end, int exclude_self,
+                           size_t *out_ids, ftype *out_dist, annb_stream stream);
+
+/* number of kernels launched through this layer since the last reset (bench.py reports it) */
+unsigned long annb_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -61,3 +61,20 @@ def oracle_mod():
     import oracle
     oracle.build()
     return oracle
+
+
+def knn_diff(got_ids, got_d, want_ids, want_d):
+    """Row-level comparison of two kNN results under the north_star rule: squared distances
+    must agree exactly; ids must agree except inside a run of EQUAL distances (an exact tie,
+    where the reference's order is an artefact of its sorting network).
+    Returns (rows whose distances differ, rows whose ids differ outside ties, rows that differ
+    only inside ties)."""
+    same_d = (np.ascontiguousarray(got_d).view(np.uint8).reshape(got_d.shape[0], -1) ==
+              np.ascontiguousarray(want_d).view(np.uint8).reshape(want_d.shape[0], -1)).all(axis=1)
+    id_neq = got_ids != want_ids
+    tie = np.zeros_like(id_neq)
+    tie[:, 1:] |= want_d[:, 1:] == want_d[:, :-1]
+    tie[:, :-1] |= want_d[:, :-1] == want_d[:, 1:]
+    hard = (id_neq & ~tie).any(axis=1)
+    soft = id_neq.any(axis=1) & ~hard
+    return int((~same_d).sum()), int(hard.sum()), int(soft.sum())
