@@ -340,7 +340,8 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
                  pad256(T * planes * 2 * 4 + 4) + pad256(T * planes * 2 * w + w) +
                  pad256(T * d_max * 4) + pad256(T * d_short * 4 + 4) +
                  pad256(annb_hash_scratch_bytes(&desc)) +
-                 pad256(n * k * 4) * 2 + pad256(n * k * w) * 3 + pad256(n * k * sizeof(size_t)) + 4096;
+                 pad256(n * k * 4) * 2 + pad256(n * k * w) * 3 + pad256(n * k * sizeof(size_t)) +
+                 pad256(annb_leaf_scratch_bytes(n)) + 8192;
   size_t group = T;                                            /* lists kept before a merge */
   while (group > 1 && fixed + group * list_bytes + 512 > free_b * 9 / 10) group--;
   if ((size_t)k * T < 16) group = T;
@@ -362,6 +363,10 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   ftype *dm_dist = arena_take(n * k * w), *dm_dist2 = arena_take(n * k * w);
   size_t *dout_ids = arena_take(n * k * sizeof(size_t));
   ftype *dout_dist = arena_take(n * k * w);
+  const size_t scratch_bytes = annb_leaf_scratch_bytes(n);
+  void *dscratch = arena_take(scratch_bytes);
+  int *dstatus = arena_take(sizeof(int));
+  CK(cudaMemsetAsync(dstatus, 0, sizeof(int), st));
 
   /* 3. upload                                                                          */
   mark(0);
@@ -429,21 +434,19 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
       }
       annb_gather_rows(dX, dorder, n, d, dXs, st);
       annb_leaf_topk(dXs, dorder, doffset, dhash + t * n, dtmax + t, n, d, d_short, k,
-                     dl_ids + j * n * k, dl_dist + j * n * k, st);
+                     dl_ids + j * n * k, dl_dist + j * n * k, dscratch, dstatus, st);
       size_t first = k * t;
       admit[j] = first >= prefix ? 0 : (int)(prefix - first < k ? prefix - first : k);
     }
-    if (tiny_merge) {
-      annb_merge_lists_tiny(dl_ids, dl_dist, (int)g, n, k, dm_ids, dm_dist, st);
-    } else {
+    {
       int corner_list = -1, corner_pos = 0;
-      if (prefix < row_len && group == T) {        /* DESIGN.md "prefix corner"          */
+      if (!tiny_merge && prefix < row_len && group == T) {      /* DESIGN.md "prefix corner" */
         corner_list = (int)(prefix / k);
         corner_pos = (int)(prefix % k);
       }
       annb_merge_lists(dl_ids, dl_dist, (int)g, admit, corner_list, corner_pos,
                        have_merged ? dm_ids : NULL, have_merged ? dm_dist : NULL, n, k,
-                       dm_ids2, dm_dist2, st);
+                       dm_ids2, dm_dist2, dscratch, scratch_bytes, dstatus, st);
       annb_u32 *ti = dm_ids; dm_ids = dm_ids2; dm_ids2 = ti;
       ftype *td = dm_dist; dm_dist = dm_dist2; dm_dist2 = td;
     }
@@ -454,12 +457,8 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   mark(5);
 
   /* 7. S5 supercharging (alg.c:313-327); the graph is the merged lists themselves        */
-  if (k * (k + 1) < 16)
-    annb_supercharge_tiny(dX, dX, dm_ids, dm_dist, dm_ids, n, d, k, 0, n, 1, dout_ids,
-                          dists_o ? dout_dist : NULL, st);
-  else
-    annb_supercharge(dX, dX, dm_ids, dm_dist, dm_ids, n, d, k, 0, n, 1, dout_ids,
-                     dists_o ? dout_dist : NULL, st);
+  annb_supercharge(dX, dX, dm_ids, dm_dist, dm_ids, n, d, k, 0, n, 1, dout_ids,
+                   dists_o ? dout_dist : NULL, dscratch, scratch_bytes, dstatus, st);
   mark(6);
 
   /* 8. results                                                                          */
@@ -470,10 +469,13 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
     CK(cudaMemcpyAsync(*dists_o, dout_dist, w * n * k, cudaMemcpyDeviceToHost, st));
   }
   annb_u32 *h_tmax = malloc(4 * T);
+  int h_status = 0;
   CK(cudaMemcpyAsync(h_tmax, dtmax, 4 * T, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&h_status, dstatus, sizeof(int), cudaMemcpyDeviceToHost, st));
   mark(7);
   CK(cudaStreamSynchronize(st));
   collect_times();
+  if (h_status) annh_fatal("%s", "scratch too small for a literal candidate row (extremely unbalanced buckets)");
   for (size_t t = 0; t < T; t++)
     if ((d_short + 1) * (size_t)h_tmax[t] < 16)
       annh_fatal("%s", "candidate rows shorter than 16 slots (n far too small for this k)");

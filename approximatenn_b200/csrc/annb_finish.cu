@@ -1,0 +1,381 @@
+// annb_finish.cu — S4 union of the per-try lists, S5 supercharging, and their literal
+// (exact-tie / short-row) counterparts.
+#include "annb_common.cuh"
+
+// =====================================================================================
+// S4: union of the per-try lists, one warp per point
+// =====================================================================================
+// The reference concatenates the per-try lists into a row of k*tries slots and runs
+// sort / kill-adjacent-duplicate-ids / sort on the first 2^floor(log2(k*tries)) of them
+// (SURVEY §8.A.3 rules 5-6).  Equal ids carry equal distances, so that is the k smallest
+// distinct ids among the admitted entries.  One corner is reproduced as well: the largest
+// admitted entry is dropped when its id equals the id in the first slot outside the
+// sorted prefix and no admitted entry is infinite ("prefix corner").
+struct MergeArgs {
+  int n_lists;
+  int admit[64];
+  int corner_list, corner_pos;
+};
+
+template <int R>
+__global__ void __launch_bounds__(256)
+merge_lists_kernel(const u32 *__restrict__ lists_ids, const FT *__restrict__ lists_dist,
+                   MergeArgs a, const u32 *__restrict__ prev_ids, const FT *__restrict__ prev_dist,
+                   size_t n, int k, u32 *__restrict__ out_ids, FT *__restrict__ out_dist,
+                   unsigned char *__restrict__ tie_flags) {
+  const int lane = threadIdx.x & 31;
+  size_t x = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (x >= n) return;
+  const u32 sentinel = (u32)n;
+  WarpList<R> best;
+  best.clear(sentinel);
+  FT tau = ft_inf();
+  FT max_v = -ft_inf();
+  u32 max_id = sentinel;
+  bool any_inf = false, tie = false;
+
+  for (int li = (prev_ids ? -1 : 0); li < a.n_lists; li++) {
+    const u32 *ids = li < 0 ? prev_ids + x * (size_t)k : lists_ids + ((size_t)li * n + x) * k;
+    const FT *dist = li < 0 ? prev_dist + x * (size_t)k : lists_dist + ((size_t)li * n + x) * k;
+    const int admit = li < 0 ? k : a.admit[li];
+    for (int base = 0; base < admit; base += 32) {
+      int e = base + lane;
+      FT mv = e < admit ? dist[e] : ft_inf();
+      u32 mi = e < admit ? ids[e] : sentinel;
+      int cnt = min(32, admit - base);
+      for (int j = 0; j < cnt; j++) {
+        FT vn = __shfl_sync(FULL, mv, j);
+        u32 idn = __shfl_sync(FULL, mi, j);
+        if (vn == ft_inf()) { any_inf = true; continue; }
+        if (vn > max_v) { max_v = vn; max_id = idn; }
+        consider<R>(best, tau, vn, idn, k, sentinel, lane, tie);
+      }
+    }
+  }
+  if (a.corner_list >= 0 && !any_inf) {
+    u32 cid = lists_ids[((size_t)a.corner_list * n + x) * k + a.corner_pos];
+    if (cid == max_id) best.remove(cid, sentinel, lane);
+  }
+#pragma unroll
+  for (int rr = 0; rr < R; rr++) {
+    int p = rr * 32 + lane;
+    if (p < k) {
+      out_ids[x * (size_t)k + p] = best.id[rr];
+      out_dist[x * (size_t)k + p] = best.v[rr];
+    }
+  }
+  if (tie && tie_flags && lane == 0) tie_flags[x] = 1;
+}
+
+// Literal row: the n_lists lists of a point side by side (k*n_lists slots), the reference's
+// network, first k slots out.  tie_flags == NULL: every row (rows shorter than 16 slots).
+__global__ void __launch_bounds__(256)
+merge_literal_kernel(const u32 *__restrict__ lists_ids, const FT *__restrict__ lists_dist,
+                     int n_lists, size_t n, int k, u32 *__restrict__ out_ids,
+                     FT *__restrict__ out_dist, const unsigned char *__restrict__ tie_flags,
+                     unsigned char *scratch, size_t scratch_bytes, int *status) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const int len = n_lists * k;
+  const size_t slab = ((size_t)len * (sizeof(u32) + sizeof(FT)) + 15) & ~(size_t)15;
+  const size_t slabs = scratch_bytes / slab;
+  if (slabs == 0) { if (warp == 0 && lane == 0) *status = 1; return; }
+  const size_t workers = slabs < nwarps ? slabs : nwarps;
+  if (warp >= workers) return;
+  FT *key = reinterpret_cast<FT *>(scratch + warp * slab);
+  u32 *ids = reinterpret_cast<u32 *>(key + len);
+
+  for (size_t base = warp * 32; base < n; base += workers * 32) {
+    size_t p = base + lane;
+    unsigned flagged = __ballot_sync(FULL, p < n && (!tie_flags || tie_flags[p]));
+    while (flagged) {
+      int src = __ffs(flagged) - 1;
+      flagged &= flagged - 1;
+      const size_t x = base + src;
+      for (int e = lane; e < len; e += 32) {
+        int t = e / k, z = e - t * k;
+        ids[e] = lists_ids[((size_t)t * n + x) * k + z];
+        key[e] = lists_dist[((size_t)t * n + x) * k + z];
+      }
+      __syncwarp();
+      warp_sort_and_uniq(ids, key, len, lane);
+      for (int i = lane; i < k; i += 32) {
+        out_ids[x * (size_t)k + i] = ids[i];
+        out_dist[x * (size_t)k + i] = key[i];
+      }
+      __syncwarp();
+    }
+  }
+}
+
+extern "C" void annb_merge_lists(const u32 *lists_ids, const FT *lists_dist, int n_lists,
+                                 const int *host_admit, int corner_list, int corner_pos,
+                                 const u32 *merged_in_ids, const FT *merged_in_dist, size_t n,
+                                 size_t k, u32 *merged_ids, FT *merged_dist, void *scratch,
+                                 size_t scratch_bytes, int *status, annb_stream stream) {
+  int regs = list_regs(k);
+  if (!regs) fatal_config("k > 256");
+  if (n_lists > 64) fatal_config("more than 64 lists per merge call");
+  unsigned char *flags = (unsigned char *)scratch;
+  unsigned char *slabs = (unsigned char *)(((uintptr_t)(flags + n) + 255) & ~(uintptr_t)255);
+  size_t slab_bytes = scratch_bytes > n + 512 ? scratch_bytes - n - 512 : 0;
+  const bool whole_row = merged_in_ids == NULL;       // the literal redo needs every list
+  if ((size_t)n_lists * k < 16) {
+    if (!whole_row) fatal_config("rows shorter than 16 slots cannot be merged incrementally");
+    merge_literal_kernel<<<148 * 2, 256, 0, stream>>>(lists_ids, lists_dist, n_lists, n, (int)k, merged_ids, merged_dist, NULL, slabs, slab_bytes, status);
+    LAUNCH_CHECK("merge_literal");
+    return;
+  }
+  MergeArgs a;
+  a.n_lists = n_lists;
+  for (int i = 0; i < n_lists; i++) a.admit[i] = host_admit[i];
+  a.corner_list = corner_list;
+  a.corner_pos = corner_pos;
+  if (whole_row) cudaMemsetAsync(flags, 0, n, stream);
+  unsigned char *f = whole_row ? flags : NULL;
+  dim3 block(256), grid(grid_for(n * 32, 256));
+  switch (regs) {
+    case 1: merge_lists_kernel<1><<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, merged_in_ids, merged_in_dist, n, (int)k, merged_ids, merged_dist, f); break;
+    case 2: merge_lists_kernel<2><<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, merged_in_ids, merged_in_dist, n, (int)k, merged_ids, merged_dist, f); break;
+    case 4: merge_lists_kernel<4><<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, merged_in_ids, merged_in_dist, n, (int)k, merged_ids, merged_dist, f); break;
+    default: merge_lists_kernel<8><<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, merged_in_ids, merged_in_dist, n, (int)k, merged_ids, merged_dist, f); break;
+  }
+  LAUNCH_CHECK("merge_lists");
+  if (whole_row) {
+    merge_literal_kernel<<<148, 256, 0, stream>>>(lists_ids, lists_dist, n_lists, n, (int)k, merged_ids, merged_dist, flags, slabs, slab_bytes, status);
+    LAUNCH_CHECK("merge_literal");
+  }
+}
+
+// =====================================================================================
+// S5: supercharging, one warp per query row
+// =====================================================================================
+// Row of the reference: [own k] ++ [list of own[0]] ++ ... ++ [list of own[k-1]], k(k+1)
+// slots; the first P2 = 2^floor(log2(k(k+1))) compete.  Own distances are carried over,
+// the others are measured here.  Same duplicate and prefix-corner rules as S4.
+
+template <int E, int R>
+__global__ void __launch_bounds__(256)
+supercharge_kernel(const FT *__restrict__ queries, const FT *__restrict__ points,
+                   const u32 *__restrict__ own_ids, const FT *__restrict__ own_dist,
+                   const u32 *__restrict__ graph, size_t n, int d, int k, size_t row_begin,
+                   size_t row_end, int exclude_self, size_t *__restrict__ out_ids,
+                   FT *__restrict__ out_dist, unsigned char *__restrict__ tie_flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  size_t x = row_begin + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (x >= row_end) return;
+  FT *tmp = reinterpret_cast<FT *>(smem_raw) + (size_t)wib * (E == 0 ? d : 0);
+  const u32 sentinel = (u32)n;
+  const int wide = k * (k + 1);
+  const int P2 = 1 << floor_log2_u((unsigned long long)wide);
+
+  WarpRow<(E ? E : 1)> q;
+  const FT *qrow = queries + x * (size_t)d;
+  if (E) q.load(qrow, lane, d);
+
+  WarpList<R> best;
+  FT max_v = -ft_inf();
+  u32 max_id = sentinel;
+  bool any_inf = false, tie = false;
+#pragma unroll
+  for (int rr = 0; rr < R; rr++) {
+    int p = rr * 32 + lane;
+    best.v[rr] = p < k ? own_dist[x * (size_t)k + p] : ft_inf();
+    best.id[rr] = p < k ? own_ids[x * (size_t)k + p] : sentinel;
+    bool fin = best.v[rr] != ft_inf();
+    if (p < k && !fin) any_inf = true;
+    if (p < k && fin && best.v[rr] > max_v) { max_v = best.v[rr]; max_id = best.id[rr]; }
+  }
+  any_inf = __any_sync(FULL, any_inf);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    FT ov = __shfl_xor_sync(FULL, max_v, o);
+    u32 oi = __shfl_xor_sync(FULL, max_id, o);
+    if (ov > max_v) { max_v = ov; max_id = oi; }
+  }
+  FT tau = best.kth(k);
+  // equal neighbours inside the own list: the network decides their final order
+#pragma unroll
+  for (int rr = 0; rr < R; rr++) {
+    FT nxt = __shfl_down_sync(FULL, best.v[rr], 1);
+    FT wrap = __shfl_sync(FULL, best.v[rr + 1 < R ? rr + 1 : rr], 0);
+    if (lane == 31) nxt = rr + 1 < R ? wrap : ft_inf();
+    if (rr * 32 + lane + 1 < k && best.v[rr] == nxt && nxt != ft_inf()) tie = true;
+  }
+  tie = __any_sync(FULL, tie);
+  u32 own_reg[R];
+#pragma unroll
+  for (int rr = 0; rr < R; rr++) own_reg[rr] = best.id[rr];
+
+  const int cand = P2 - k;                     // slots k .. P2-1 of the row
+  for (int base = 0; base < cand; base += 32) {
+    int c = base + lane;
+    int j = c < cand ? c / k : 0;
+    int z = c - j * k;
+    u32 oj = sentinel;
+#pragma unroll
+    for (int rr = 0; rr < R; rr++) {
+      u32 got = __shfl_sync(FULL, own_reg[rr], j & 31);
+      if (rr == (j >> 5)) oj = got;
+    }
+    u32 cid = (c < cand && oj < sentinel) ? graph[(size_t)oj * k + z] : sentinel;
+    int cnt = min(32, cand - base);
+    for (int i = 0; i < cnt; i++) {
+      u32 idn = __shfl_sync(FULL, cid, i);
+      if (idn >= sentinel || (exclude_self && idn == (u32)x)) { any_inf = true; continue; }
+      FT dist;
+      if (E) {
+        WarpRow<(E ? E : 1)> cr;
+        cr.load(points + (size_t)idn * d, lane, d);
+        dist = __shfl_sync(FULL, warp_sqdist<(E ? E : 1)>(q, cr, d), 0);
+      } else {
+        dist = generic_sqdist(qrow, points + (size_t)idn * d, d, tmp, lane);
+      }
+      if (dist > max_v) { max_v = dist; max_id = idn; }
+      consider<R>(best, tau, dist, idn, k, sentinel, lane, tie);
+    }
+  }
+  if (P2 < wide && !any_inf) {
+    int c = P2 - k, j = c / k, z = c - j * k;
+    u32 oj = sentinel;
+#pragma unroll
+    for (int rr = 0; rr < R; rr++) {
+      u32 got = __shfl_sync(FULL, own_reg[rr], j & 31);
+      if (rr == (j >> 5)) oj = got;
+    }
+    u32 cid = oj < sentinel ? graph[(size_t)oj * k + z] : sentinel;
+    if (cid == max_id) best.remove(cid, sentinel, lane);
+  }
+  size_t orow = x - row_begin;
+#pragma unroll
+  for (int rr = 0; rr < R; rr++) {
+    int p = rr * 32 + lane;
+    if (p < k) {
+      out_ids[orow * (size_t)k + p] = (size_t)best.id[rr];
+      if (out_dist) out_dist[orow * (size_t)k + p] = best.v[rr];
+    }
+  }
+  if (tie && tie_flags && lane == 0) tie_flags[orow] = 1;
+}
+
+// Literal row of k(k+1) slots (supercharge + compdists + sort_and_uniq, alg.c:313-327).
+template <int E>
+__global__ void __launch_bounds__(256)
+supercharge_literal_kernel(const FT *__restrict__ queries, const FT *__restrict__ points,
+                           const u32 *__restrict__ own_ids, const FT *__restrict__ own_dist,
+                           const u32 *__restrict__ graph, size_t n, int d, int k, size_t row_begin,
+                           size_t row_end, int exclude_self, size_t *__restrict__ out_ids,
+                           FT *__restrict__ out_dist, const unsigned char *__restrict__ tie_flags,
+                           unsigned char *scratch, size_t scratch_bytes, int *status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  FT *tmp = reinterpret_cast<FT *>(smem_raw) + (size_t)wib * (E == 0 ? d : 0);
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const int wide = k * (k + 1);
+  const size_t slab = ((size_t)wide * (sizeof(u32) + sizeof(FT)) + 15) & ~(size_t)15;
+  const size_t slabs = scratch_bytes / slab;
+  if (slabs == 0) { if (warp == 0 && lane == 0) *status = 1; return; }
+  const size_t workers = slabs < nwarps ? slabs : nwarps;
+  if (warp >= workers) return;
+  FT *key = reinterpret_cast<FT *>(scratch + warp * slab);
+  u32 *ids = reinterpret_cast<u32 *>(key + wide);
+  const u32 sentinel = (u32)n;
+  const size_t rows = row_end - row_begin;
+
+  for (size_t base = warp * 32; base < rows; base += workers * 32) {
+    size_t p = base + lane;
+    unsigned flagged = __ballot_sync(FULL, p < rows && (!tie_flags || tie_flags[p]));
+    while (flagged) {
+      int src = __ffs(flagged) - 1;
+      flagged &= flagged - 1;
+      const size_t orow = base + src, x = row_begin + orow;
+      for (int e = lane; e < k; e += 32) {
+        ids[e] = own_ids[x * (size_t)k + e];
+        key[e] = own_dist[x * (size_t)k + e];
+      }
+      __syncwarp();
+      for (int e = lane; e < k * k; e += 32) {                    // compute.cl:252-263
+        int j = e / k, z = e - j * k;
+        u32 oj = ids[j];
+        ids[k + e] = oj < sentinel ? graph[(size_t)oj * k + z] : sentinel;
+      }
+      __syncwarp();
+      for (int e = k; e < wide; e++) {
+        u32 cid = ids[e];
+        FT dist = ft_inf();
+        if (cid < sentinel && !(exclude_self && cid == (u32)x))
+          dist = row_sqdist<E>(queries + x * (size_t)d, points + (size_t)cid * d, d, tmp, lane);
+        if (lane == 0) key[e] = dist;
+      }
+      __syncwarp();
+      warp_sort_and_uniq(ids, key, wide, lane);
+      for (int i = lane; i < k; i += 32) {
+        out_ids[orow * (size_t)k + i] = (size_t)ids[i];
+        if (out_dist) out_dist[orow * (size_t)k + i] = key[i];
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int E>
+static void launch_supercharge(int regs, size_t smem, annb_stream stream, const FT *queries,
+                               const FT *points, const u32 *own_ids, const FT *own_dist,
+                               const u32 *graph, size_t n, int d, int k, size_t rb, size_t re, int ex,
+                               size_t *out_ids, FT *out_dist, unsigned char *flags,
+                               unsigned char *slabs, size_t slab_bytes, int *status, bool all_literal) {
+  dim3 block(256), grid(grid_for((re - rb) * 32, 256));
+#define SC_CASE(R)                                                                               \
+  {                                                                                              \
+    if (smem > 48 * 1024)                                                                        \
+      cudaFuncSetAttribute(supercharge_kernel<E, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    supercharge_kernel<E, R><<<grid, block, smem, stream>>>(queries, points, own_ids, own_dist, graph, n, d, k, rb, re, ex, out_ids, out_dist, flags); \
+  }
+  if (!all_literal) {
+    switch (regs) {
+      case 1: SC_CASE(1) break;
+      case 2: SC_CASE(2) break;
+      case 4: SC_CASE(4) break;
+      default: SC_CASE(8) break;
+    }
+    LAUNCH_CHECK("supercharge");
+  }
+#undef SC_CASE
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(supercharge_literal_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  supercharge_literal_kernel<E><<<all_literal ? 148 * 2 : 148, 256, smem, stream>>>(
+      queries, points, own_ids, own_dist, graph, n, d, k, rb, re, ex, out_ids, out_dist,
+      all_literal ? NULL : flags, slabs, slab_bytes, status);
+  LAUNCH_CHECK("supercharge_literal");
+}
+
+extern "C" void annb_supercharge(const FT *queries, const FT *points, const u32 *own_ids,
+                                 const FT *own_dist, const u32 *graph, size_t n, size_t d, size_t k,
+                                 size_t row_begin, size_t row_end, int exclude_self,
+                                 size_t *out_ids, FT *out_dist, void *scratch, size_t scratch_bytes,
+                                 int *status, annb_stream stream) {
+  if (row_end <= row_begin) return;
+  int regs = list_regs(k);
+  if (!regs) fatal_config("k > 256");
+  int mode = row_mode(d);
+  size_t smem = mode ? 0 : 8 * d * sizeof(FT);
+  if (smem > 200 * 1024) fatal_config("d too large for the generic distance path");
+  const size_t rows = row_end - row_begin;
+  unsigned char *flags = (unsigned char *)scratch;
+  unsigned char *slabs = (unsigned char *)(((uintptr_t)(flags + rows) + 255) & ~(uintptr_t)255);
+  size_t slab_bytes = scratch_bytes > rows + 512 ? scratch_bytes - rows - 512 : 0;
+  const bool all_literal = k * (k + 1) < 16;      // the network degenerates: literal rows only
+  if (!all_literal) cudaMemsetAsync(flags, 0, rows, stream);
+#define SC_ARGS regs, smem, stream, queries, points, own_ids, own_dist, graph, n, (int)d, (int)k, row_begin, row_end, exclude_self, out_ids, out_dist, flags, slabs, slab_bytes, status, all_literal
+  switch (mode) {
+    case 0: launch_supercharge<0>(SC_ARGS); break;
+    case 1: launch_supercharge<1>(SC_ARGS); break;
+    case 2: launch_supercharge<2>(SC_ARGS); break;
+    case 4: launch_supercharge<4>(SC_ARGS); break;
+    default: launch_supercharge<8>(SC_ARGS); break;
+  }
+#undef SC_ARGS
+}

@@ -1,0 +1,552 @@
+// annb_leaf.cu — S3: candidate distances + per-point k best of one try.
+//
+// Three kernels behind annb_leaf_topk():
+//   leaf_topk_tile_kernel   the fast path.  One warp per bucket: every point of a bucket
+//                           has the same candidates (slots p < P of [b, b^1, b^2, b^4, ...]),
+//                           so candidate rows are staged once per bucket in shared memory
+//                           (cp.async, double buffered) and broadcast to lanes that each hold
+//                           one query row in registers.  Distances follow the reference's
+//                           summation tree exactly; each lane keeps its k best in registers
+//                           and folds batches in with sorting networks.
+//   leaf_topk_warp_kernel   any d, any k <= 256: one warp per point, cooperative distance.
+//   leaf_literal_kernel     redoes the (rare) rows in which an exact distance tie could
+//                           matter with the reference's literal row + sorting network.
+#include "annb_common.cuh"
+
+// =====================================================================================
+// generic: one warp per point
+// =====================================================================================
+
+template <int E, int R>
+__global__ void __launch_bounds__(256)
+leaf_topk_warp_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
+                      const u32 *__restrict__ offset, const u32 *__restrict__ hash,
+                      const u32 *__restrict__ tmax_p, size_t n, int d, int d_short, int k,
+                      u32 *__restrict__ list_ids, FT *__restrict__ list_dist,
+                      unsigned char *__restrict__ tie_flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  size_t r = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // sorted position
+  if (r >= n) return;
+  FT *tmp = reinterpret_cast<FT *>(smem_raw) + (size_t)wib * (E == 0 ? d : 0);
+  const u32 sentinel = (u32)n;
+  const u32 me = order[r];
+  const u32 h = hash[me];
+  const unsigned long long tmax = *tmax_p;
+  const unsigned long long L = (unsigned long long)(d_short + 1) * tmax;
+  const unsigned long long P = 1ull << floor_log2_u(L);
+
+  WarpRow<(E ? E : 1)> q;
+  const FT *qrow = sp + r * (size_t)d;
+  if (E) q.load(qrow, lane, d);
+  WarpList<R> best;
+  best.clear(sentinel);
+  FT tau = ft_inf();
+  bool tie = false;
+
+  for (int y = 0; y <= d_short; y++) {
+    unsigned long long first_slot = (unsigned long long)y * tmax;
+    if (first_slot >= P) break;
+    u32 b = h ^ (y ? (1u << (y - 1)) : 0u);
+    u32 beg = offset[b], cnt = offset[b + 1] - beg;
+    unsigned long long room = P - first_slot;
+    u32 inc = cnt < room ? cnt : (u32)room;
+    for (u32 c = 0; c < inc; c++) {
+      size_t row = (size_t)beg + c;
+      if (row == r) continue;                                  // self (compute.cl:145)
+      FT dist;
+      if (E) {
+        WarpRow<(E ? E : 1)> cr;
+        cr.load(sp + row * (size_t)d, lane, d);
+        dist = __shfl_sync(FULL, warp_sqdist<(E ? E : 1)>(q, cr, d), 0);
+      } else {
+        dist = generic_sqdist(qrow, sp + row * (size_t)d, d, tmp, lane);
+      }
+      consider<R>(best, tau, dist, order[row], k, sentinel, lane, tie);
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < R; rr++) {
+    int p = rr * 32 + lane;
+    if (p < k) {
+      list_ids[(size_t)me * k + p] = best.id[rr];
+      list_dist[(size_t)me * k + p] = best.v[rr];
+    }
+  }
+  if (tie && lane == 0) tie_flags[me] = 1;
+}
+
+// =====================================================================================
+// fast path: one warp per bucket, queries in registers, candidates broadcast from smem
+// =====================================================================================
+
+static constexpr int VW = 16 / sizeof(FT);          // elements per 16-byte vector
+static constexpr int TILE_CH = 16;                  // candidate rows per staged chunk
+static constexpr int TILE_WARPS = 4;
+
+struct __align__(16) Vec16 { FT x[VW]; };
+
+// Partial sums of the reference's tree (compute.cl:160-167), VW lanes wide.  Node (LEN, OFF)
+// is elements OFF..OFF+VW-1 of the array at the stage where it has LEN entries:
+// V_LEN[z] = V_2LEN[z] + V_2LEN[z + LEN]; the leaves (LEN == D) are squared differences.
+template <int D, int LEN, int OFF>
+struct TreeNode {
+  static __device__ __forceinline__ void eval(const FT (&q)[D], const FT *crow, FT (&out)[VW]) {
+    FT a[VW], b[VW];
+    TreeNode<D, 2 * LEN, OFF>::eval(q, crow, a);
+    TreeNode<D, 2 * LEN, OFF + LEN>::eval(q, crow, b);
+#pragma unroll
+    for (int w = 0; w < VW; w++) out[w] = a[w] + b[w];
+  }
+};
+template <int D, int OFF>
+struct TreeNode<D, D, OFF> {
+  static __device__ __forceinline__ void eval(const FT (&q)[D], const FT *crow, FT (&out)[VW]) {
+    Vec16 c = *reinterpret_cast<const Vec16 *>(crow + OFF);
+#pragma unroll
+    for (int w = 0; w < VW; w++) {
+      FT df = q[OFF + w] - c.x[w];
+      out[w] = df * df;
+    }
+  }
+};
+
+template <int D>
+__device__ __forceinline__ FT tile_sqdist(const FT (&q)[D], const FT *crow) {
+  FT v[VW];
+  TreeNode<D, VW, 0>::eval(q, crow, v);
+#pragma unroll
+  for (int h = VW / 2; h >= 1; h >>= 1)
+#pragma unroll
+    for (int w = 0; w < h; w++) v[w] = v[w] + v[w + h];
+  return v[0];
+}
+
+#define CE_ASC(da, ia, db, ib)                                    \
+  {                                                               \
+    bool sw_ = (da) > (db);                                       \
+    FT lo_ = sw_ ? (db) : (da), hi_ = sw_ ? (da) : (db);          \
+    u32 li_ = sw_ ? (ib) : (ia), hj_ = sw_ ? (ia) : (ib);         \
+    (da) = lo_; (db) = hi_; (ia) = li_; (ib) = hj_;               \
+  }
+
+// list <- the KC smallest of list ∪ batch, ascending.  `tie` is raised when the smallest
+// discarded value equals the largest kept one (an exact tie on the boundary).
+template <int KC>
+__device__ __forceinline__ void fold_batch(FT (&ld)[KC], u32 (&li)[KC], FT (&bd)[KC], u32 (&bi)[KC],
+                                           bool sort_batch, bool &tie) {
+  if (sort_batch) {
+#pragma unroll
+    for (int kk = 2; kk <= KC; kk <<= 1)
+#pragma unroll
+      for (int j = kk >> 1; j > 0; j >>= 1)
+#pragma unroll
+        for (int i = 0; i < KC; i++) {
+          int l = i ^ j;
+          if (l > i) {
+            if ((i & kk) == 0) CE_ASC(bd[i], bi[i], bd[l], bi[l])
+            else CE_ASC(bd[l], bi[l], bd[i], bi[i])
+          }
+        }
+  }
+  FT mdisc = ft_inf();
+#pragma unroll
+  for (int i = 0; i < KC; i++) {
+    FT a = ld[i], b = bd[KC - 1 - i];
+    bool tb = b < a;
+    mdisc = fmin(mdisc, tb ? a : b);
+    ld[i] = tb ? b : a;
+    li[i] = tb ? bi[KC - 1 - i] : li[i];
+  }
+#pragma unroll
+  for (int j = KC >> 1; j > 0; j >>= 1)
+#pragma unroll
+    for (int i = 0; i < KC; i++) {
+      int l = i ^ j;
+      if (l > i) CE_ASC(ld[i], li[i], ld[l], li[l])
+    }
+  if (mdisc == ld[KC - 1] && mdisc != ft_inf()) tie = true;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <int D, int KC>
+struct TileSmem {
+  static constexpr int RS = D + VW;                                   // padded row stride
+  static constexpr size_t rows_bytes = 2ull * TILE_CH * RS * sizeof(FT);
+  static constexpr size_t cid_bytes = 2ull * TILE_CH * sizeof(u32);
+  static constexpr size_t batch_bytes = (size_t)KC * 32 * (sizeof(FT) + sizeof(u32));
+  static constexpr size_t seg_bytes = (33 + 32) * sizeof(u32);
+  static constexpr size_t per_warp = (rows_bytes + cid_bytes + batch_bytes + seg_bytes + 15) & ~(size_t)15;
+};
+
+template <int D, int KC>
+__global__ void __launch_bounds__(TILE_WARPS * 32)
+leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
+                      const u32 *__restrict__ offset, const u32 *__restrict__ tmax_p, size_t n,
+                      size_t buckets, int d_short, int k, u32 *__restrict__ list_ids,
+                      FT *__restrict__ list_dist, unsigned char *__restrict__ tie_flags) {
+  typedef TileSmem<D, KC> SM;
+  constexpr int RS = SM::RS;
+  constexpr int PPR = D / VW;                                          // 16-byte pieces per row
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  unsigned char *mine = smem_raw + (size_t)wib * SM::per_warp;
+  FT *rows = reinterpret_cast<FT *>(mine);                             // [2][CH][RS]
+  u32 *cids = reinterpret_cast<u32 *>(mine + SM::rows_bytes);          // [2][CH]
+  FT *bdist = reinterpret_cast<FT *>(mine + SM::rows_bytes + SM::cid_bytes);   // [KC][32]
+  u32 *bidx = reinterpret_cast<u32 *>(bdist + KC * 32);                // [KC][32]
+  u32 *segpos = bidx + KC * 32;                                        // [33]
+  u32 *segrow = segpos + 33;                                           // [32]
+
+  const size_t b = (size_t)blockIdx.x * TILE_WARPS + wib;
+  if (b >= buckets) return;
+  const u32 beg = offset[b], Q = offset[b + 1] - beg;
+  if (Q == 0) return;
+  const u32 sentinel = (u32)n;
+  const unsigned long long tmax = *tmax_p;
+  const unsigned long long L = (unsigned long long)(d_short + 1) * tmax;
+  const unsigned long long P = 1ull << floor_log2_u(L);
+
+  // candidate segments: lane y describes bucket b ^ f_y (compute.cl:238-246 + prefix rule)
+  {
+    u32 inc = 0, srow = 0;
+    unsigned long long first_slot = (unsigned long long)lane * tmax;
+    if (lane <= d_short && first_slot < P) {
+      u32 cb = (u32)b ^ (lane ? (1u << (lane - 1)) : 0u);
+      u32 sb = offset[cb], cnt = offset[cb + 1] - sb;
+      unsigned long long room = P - first_slot;
+      inc = cnt < room ? cnt : (u32)room;
+      srow = sb;
+    }
+    u32 incl = inc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      u32 up = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += up;
+    }
+    segpos[lane] = incl - inc;
+    segrow[lane] = srow;
+    if (lane == 31) segpos[32] = incl;
+  }
+  __syncwarp();
+  const u32 C = segpos[32];
+  const u32 nchunks = (C + TILE_CH - 1) / TILE_CH;
+
+  for (u32 qbase = 0; qbase < Q; qbase += 32) {
+    const u32 Qp = min(32u, Q - qbase);
+    const int S = Qp <= 4 ? 8 : Qp <= 8 ? 4 : Qp <= 16 ? 2 : 1;       // candidate slices
+    const int per = TILE_CH / S;
+    const bool active = lane < (int)(Qp * S);
+    const int s = active ? lane / (int)Qp : 0;
+    const int qi = active ? lane - s * (int)Qp : 0;
+    const size_t my_row = (size_t)beg + qbase + qi;
+    const u32 my_id = order[my_row];
+
+    FT q[D];
+    {
+      const Vec16 *src = reinterpret_cast<const Vec16 *>(sp + my_row * (size_t)D);
+#pragma unroll
+      for (int v = 0; v < PPR; v++) {
+        Vec16 t = src[v];
+#pragma unroll
+        for (int w = 0; w < VW; w++) q[v * VW + w] = t.x[w];
+      }
+    }
+    FT ld[KC];
+    u32 li[KC];
+#pragma unroll
+    for (int i = 0; i < KC; i++) { ld[i] = ft_inf(); li[i] = sentinel; }
+    bool tie = false;
+    int cnt = 0;
+
+    auto stage_chunk = [&](u32 c, int buf) {
+      // lanes 0..15 locate the rows of this chunk; every lane then copies 16-byte pieces
+      u32 j = c * TILE_CH + (lane & (TILE_CH - 1));
+      u32 grow = 0;
+      if (j < C) {
+        int y = 0;
+        while (j >= segpos[y + 1]) y++;
+        grow = segrow[y] + (j - segpos[y]);
+      }
+      if (lane < TILE_CH) {
+        if (j < C) cp_async4(&cids[buf * TILE_CH + lane], order + grow);
+        else cids[buf * TILE_CH + lane] = sentinel;
+      }
+      FT *dst = rows + (size_t)buf * TILE_CH * RS;
+#pragma unroll
+      for (int it = 0; it < (TILE_CH * PPR + 31) / 32; it++) {
+        int p = lane + 32 * it;
+        int r = p / PPR, col = p - r * PPR;
+        u32 gr = __shfl_sync(FULL, grow, r & (TILE_CH - 1));
+        if (p < TILE_CH * PPR) cp_async16(dst + r * RS + col * VW, sp + (size_t)gr * D + col * VW);
+      }
+      cp_async_commit();
+    };
+
+    if (nchunks) stage_chunk(0, 0);
+    for (u32 c = 0; c < nchunks; c++) {
+      const int buf = c & 1;
+      if (c + 1 < nchunks) { stage_chunk(c + 1, buf ^ 1); cp_async_wait<1>(); }
+      else cp_async_wait<0>();
+      __syncwarp();
+      const FT *crows = rows + (size_t)buf * TILE_CH * RS;
+      for (int i = 0; i < per; i++) {
+        const int j = s + S * i;
+        const u32 cid = cids[buf * TILE_CH + j];
+        FT dist = tile_sqdist<D>(q, crows + j * RS);
+        if (cid == sentinel || cid == my_id) dist = ft_inf();        // pad / self (compute.cl:144-149)
+        bdist[cnt * 32 + lane] = dist;
+        bidx[cnt * 32 + lane] = cid;
+        cnt++;
+      }
+      if (cnt == KC) {
+        FT bd[KC];
+        u32 bi[KC];
+#pragma unroll
+        for (int i = 0; i < KC; i++) { bd[i] = bdist[i * 32 + lane]; bi[i] = bidx[i * 32 + lane]; }
+        fold_batch<KC>(ld, li, bd, bi, true, tie);
+        cnt = 0;
+      }
+      __syncwarp();
+    }
+    if (cnt > 0) {
+      FT bd[KC];
+      u32 bi[KC];
+#pragma unroll
+      for (int i = 0; i < KC; i++) {
+        bool have = i < cnt;
+        bd[i] = have ? bdist[i * 32 + lane] : ft_inf();
+        bi[i] = have ? bidx[i * 32 + lane] : sentinel;
+      }
+      fold_batch<KC>(ld, li, bd, bi, true, tie);
+    }
+    // fold the slices of each query together (lists are sorted: no batch sort needed)
+    for (int hs = S >> 1; hs >= 1; hs >>= 1) {
+      FT bd[KC];
+      u32 bi[KC];
+      int src = lane + hs * (int)Qp;
+      src = src < 32 ? src : lane;
+#pragma unroll
+      for (int i = 0; i < KC; i++) {
+        bd[i] = __shfl_sync(FULL, ld[i], src);
+        bi[i] = __shfl_sync(FULL, li[i], src);
+      }
+      bool other_tie = __shfl_sync(FULL, (int)tie, src);
+      if (s < hs) {
+        fold_batch<KC>(ld, li, bd, bi, false, tie);
+        tie |= other_tie;
+      }
+    }
+    if (active && s == 0) {
+#pragma unroll
+      for (int i = 0; i < KC; i++)
+        if (i < k) {
+          list_ids[(size_t)my_id * k + i] = li[i];
+          list_dist[(size_t)my_id * k + i] = ld[i];
+          if (i + 1 < KC && ld[i] == ld[i + 1] && ld[i] != ft_inf()) tie = true;
+        }
+      if (tie) tie_flags[my_id] = 1;
+    }
+    __syncwarp();
+  }
+}
+
+// =====================================================================================
+// literal rows for flagged points (exact ties)
+// =====================================================================================
+// Builds the reference's candidate row of one point (all (d_short+1)*tmax slots, pads and
+// self at +inf), runs its sorting network / duplicate rule / sorting network, and rewrites
+// the point's list.  Row storage is a slab of `slab_slots` (id, key) slots per warp in
+// global scratch; warps without a slab (scratch too small for them) do nothing, and if not
+// even one fits, *status is set.
+
+template <int E>
+__global__ void __launch_bounds__(256)
+leaf_literal_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
+                    const u32 *__restrict__ offset, const u32 *__restrict__ hash,
+                    const u32 *__restrict__ rank_of, const u32 *__restrict__ tmax_p, size_t n, int d,
+                    int d_short, int k, u32 *__restrict__ list_ids, FT *__restrict__ list_dist,
+                    const unsigned char *__restrict__ tie_flags, unsigned char *scratch,
+                    size_t scratch_bytes, int *status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  FT *tmp = reinterpret_cast<FT *>(smem_raw) + (size_t)wib * (E == 0 ? d : 0);
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const unsigned long long tmax = *tmax_p;
+  const size_t L = (size_t)(d_short + 1) * tmax;
+  const size_t slab = (L * (sizeof(u32) + sizeof(FT)) + 15) & ~(size_t)15;
+  const size_t slabs = slab ? scratch_bytes / slab : 0;
+  if (slabs == 0) { if (warp == 0 && lane == 0) *status = 1; return; }
+  const size_t workers = slabs < nwarps ? slabs : nwarps;
+  if (warp >= workers) return;
+  FT *key = reinterpret_cast<FT *>(scratch + warp * slab);
+  u32 *ids = reinterpret_cast<u32 *>(key + L);
+  const u32 sentinel = (u32)n;
+
+  for (size_t base = warp * 32; base < n; base += workers * 32) {
+    size_t p = base + lane;
+    unsigned flagged = __ballot_sync(FULL, p < n && tie_flags[p]);
+    while (flagged) {
+      int src = __ffs(flagged) - 1;
+      flagged &= flagged - 1;
+      const u32 x = (u32)(base + src);
+      const u32 h = hash[x];
+      const size_t xr = rank_of[x];                               // sorted position of x
+      for (int y = 0; y <= d_short; y++) {
+        u32 b = h ^ (y ? (1u << (y - 1)) : 0u);
+        u32 beg = offset[b], cnt = offset[b + 1] - beg;
+        for (u32 z = lane; z < (u32)tmax; z += 32) ids[(size_t)y * tmax + z] = z < cnt ? order[beg + z] : sentinel;
+        for (u32 z = 0; z < (u32)tmax; z++) {
+          FT dist = ft_inf();
+          if (z < cnt && (size_t)beg + z != xr)
+            dist = row_sqdist<E>(sp + xr * (size_t)d, sp + ((size_t)beg + z) * d, d, tmp, lane);
+          if (lane == 0) key[(size_t)y * tmax + z] = dist;
+        }
+      }
+      __syncwarp();
+      warp_sort_and_uniq(ids, key, (int)L, lane);
+      for (int i = lane; i < k; i += 32) {
+        list_ids[(size_t)x * k + i] = ids[i];
+        list_dist[(size_t)x * k + i] = key[i];
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// rank_of[order[r]] = r
+__global__ void invert_order_kernel(const u32 *__restrict__ order, size_t n, u32 *rank_of) {
+  size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) rank_of[order[r]] = (u32)r;
+}
+
+// =====================================================================================
+// launcher
+// =====================================================================================
+
+template <int E>
+static void launch_warp_r(int regs, dim3 grid, dim3 block, size_t smem, annb_stream stream,
+                          const FT *sp, const u32 *order, const u32 *offset, const u32 *hash,
+                          const u32 *tmax, size_t n, int d, int d_short, int k, u32 *ids, FT *dist,
+                          unsigned char *flags) {
+#define WARP_CASE(R)                                                                             \
+  {                                                                                              \
+    if (smem > 48 * 1024)                                                                        \
+      cudaFuncSetAttribute(leaf_topk_warp_kernel<E, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    leaf_topk_warp_kernel<E, R><<<grid, block, smem, stream>>>(sp, order, offset, hash, tmax, n, d, d_short, k, ids, dist, flags); \
+  }
+  switch (regs) {
+    case 1: WARP_CASE(1) break;
+    case 2: WARP_CASE(2) break;
+    case 4: WARP_CASE(4) break;
+    default: WARP_CASE(8) break;
+  }
+#undef WARP_CASE
+}
+
+template <int D, int KC>
+static void launch_tile(annb_stream stream, const FT *sp, const u32 *order, const u32 *offset,
+                        const u32 *tmax, size_t n, size_t buckets, int d_short, int k, u32 *ids,
+                        FT *dist, unsigned char *flags) {
+  size_t smem = TileSmem<D, KC>::per_warp * TILE_WARPS;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(leaf_topk_tile_kernel<D, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  unsigned grid = (unsigned)((buckets + TILE_WARPS - 1) / TILE_WARPS);
+  leaf_topk_tile_kernel<D, KC><<<grid, TILE_WARPS * 32, smem, stream>>>(sp, order, offset, tmax, n, buckets, d_short, k, ids, dist, flags);
+}
+
+// returns false when no tiled instantiation covers (d, k)
+static bool try_launch_tile(annb_stream stream, const FT *sp, const u32 *order, const u32 *offset,
+                            const u32 *tmax, size_t n, size_t buckets, size_t d, int d_short,
+                            size_t k, u32 *ids, FT *dist, unsigned char *flags) {
+  const char *off = getenv("ANN_B200_NO_TILE");
+  if (off && *off && *off != '0') return false;
+  if (d_short > 31) return false;
+#define TILE_CASE(DD, KK) { launch_tile<DD, KK>(stream, sp, order, offset, tmax, n, buckets, d_short, (int)k, ids, dist, flags); return true; }
+  if (k <= 16) {
+    if (d == 16) TILE_CASE(16, 16)
+    if (d == 32) TILE_CASE(32, 16)
+#ifdef USE_FLOAT
+    if (d == 64) TILE_CASE(64, 16)
+#endif
+  }
+#ifdef USE_FLOAT
+  else if (k <= 32) {
+    if (d == 16) TILE_CASE(16, 32)
+    if (d == 32) TILE_CASE(32, 32)
+  }
+#endif
+#undef TILE_CASE
+  return false;
+}
+
+extern "C" size_t annb_leaf_scratch_bytes(size_t n) { return n * sizeof(u32) + n + (64u << 20) + 256; }
+
+extern "C" void annb_leaf_topk(const FT *sorted_points, const u32 *order, const u32 *offset,
+                               const u32 *hash, const u32 *tmax, size_t n, size_t d,
+                               size_t d_short, size_t k, u32 *list_ids, FT *list_dist,
+                               void *scratch, int *status, annb_stream stream) {
+  int regs = list_regs(k);
+  if (!regs) fatal_config("k > 256");
+  // scratch layout: rank_of[n] | flags[n] | literal-row slabs
+  u32 *rank_of = (u32 *)scratch;
+  unsigned char *flags = (unsigned char *)(rank_of + n);
+  unsigned char *slabs = (unsigned char *)(((uintptr_t)(flags + n) + 255) & ~(uintptr_t)255);
+  size_t slab_bytes = 64u << 20;
+  cudaMemsetAsync(flags, 0, n, stream);
+  const size_t buckets = (size_t)1 << d_short;
+  int mode = row_mode(d);
+  size_t gsmem = mode ? 0 : 8 * d * sizeof(FT);
+  if (gsmem > 200 * 1024) fatal_config("d too large for the generic distance path");
+
+  if (!try_launch_tile(stream, sorted_points, order, offset, tmax, n, buckets, d, (int)d_short, k,
+                       list_ids, list_dist, flags)) {
+    dim3 block(256), grid(grid_for(n * 32, 256));
+#define W_ARGS regs, grid, block, gsmem, stream, sorted_points, order, offset, hash, tmax, n, (int)d, (int)d_short, (int)k, list_ids, list_dist, flags
+    switch (mode) {
+      case 0: launch_warp_r<0>(W_ARGS); break;
+      case 1: launch_warp_r<1>(W_ARGS); break;
+      case 2: launch_warp_r<2>(W_ARGS); break;
+      case 4: launch_warp_r<4>(W_ARGS); break;
+      default: launch_warp_r<8>(W_ARGS); break;
+    }
+#undef W_ARGS
+  }
+  LAUNCH_CHECK("leaf_topk");
+
+  invert_order_kernel<<<grid_for(n, 256), 256, 0, stream>>>(order, n, rank_of);
+  LAUNCH_CHECK("invert_order");
+  dim3 lblock(256), lgrid(148);
+#define L_ARGS sorted_points, order, offset, hash, rank_of, tmax, n, (int)d, (int)d_short, (int)k, list_ids, list_dist, flags, slabs, slab_bytes, status
+#define L_CASE(EE)                                                                                \
+  {                                                                                               \
+    if (gsmem > 48 * 1024)                                                                        \
+      cudaFuncSetAttribute(leaf_literal_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem); \
+    leaf_literal_kernel<EE><<<lgrid, lblock, gsmem, stream>>>(L_ARGS);                            \
+  }
+  switch (mode) {
+    case 0: L_CASE(0) break;
+    case 1: L_CASE(1) break;
+    case 2: L_CASE(2) break;
+    case 4: L_CASE(4) break;
+    default: L_CASE(8) break;
+  }
+#undef L_CASE
+#undef L_ARGS
+  LAUNCH_CHECK("leaf_literal");
+}

@@ -1,0 +1,372 @@
+// annb_prepare.cu — S0 column means, S1 transform + sign hash, S2 bucket tables.
+// See annb_common.cuh / include/annb200.h; compiled with -fmad=false (bit-exact contract).
+#include "annb_common.cuh"
+
+unsigned long annb_g_launches = 0;
+
+extern "C" unsigned long annb_launch_count(int reset) {
+  unsigned long v = annb_g_launches;
+  if (reset) annb_g_launches = 0;
+  return v;
+}
+
+// =====================================================================================
+// S0: column means
+// =====================================================================================
+
+__global__ void fold_rows_kernel(const FT *__restrict__ src, FT *dst, size_t half, size_t len,
+                                 size_t d, int first) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= half * d) return;
+  FT a = src[e], b = src[e + half * d];
+  FT extra = (e < d && (len & 1)) ? src[(len - 1) * d + e] : (FT)0;
+  dst[e] = first ? (a + b) + extra : a + (b + extra);
+}
+
+__global__ void scale_means_kernel(const FT *acc, size_t n, size_t d, FT *mean) {
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < d) mean[c] = acc[c] / (FT)n;
+}
+
+extern "C" void annb_fold_rows(const FT *src, FT *dst, size_t len, size_t d, int first,
+                               annb_stream stream) {
+  size_t half = len / 2;
+  if (half == 0) return;
+  fold_rows_kernel<<<grid_for(half * d, 256), 256, 0, stream>>>(src, dst, half, len, d, first);
+  LAUNCH_CHECK("fold_rows");
+}
+
+extern "C" void annb_scale_means(const FT *acc, size_t n, size_t d, FT *mean, annb_stream stream) {
+  scale_means_kernel<<<grid_for(d, 128), 128, 0, stream>>>(acc, n, d, mean);
+  LAUNCH_CHECK("scale_means");
+}
+
+// =====================================================================================
+// S1: transform + hash
+// =====================================================================================
+// One CTA owns TP consecutive points; thread t owns point t of the tile.  The tile lives
+// transposed in memory, element (coordinate c, point t) at c*(TP+1)+t, so that every
+// per-coordinate access of a warp is one conflict-free shared-memory wavefront while the
+// coordinate index stays a run-time value (the sub-permutations are data).  Two planes:
+//   V[d]     the centred row, rotated in place by the "before" sweeps
+//   Z[d_max] the embedded row, Walsh-Hadamard and "after" sweeps in place
+// The planes sit in shared memory when they fit, otherwise in a global scratch slab.
+
+template <int TP>
+__global__ void __launch_bounds__(TP)
+hash_points_kernel(const FT *__restrict__ points, const FT *__restrict__ mean,
+                   annb_transform_desc t, u32 *__restrict__ hash, FT *gscratch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int LD = TP + 1;
+  const size_t d = t.d, dm = t.d_max;
+  FT *V = gscratch ? gscratch + (size_t)blockIdx.x * (d + dm) * LD : reinterpret_cast<FT *>(smem_raw);
+  FT *Z = V + d * LD;
+  const int tid = threadIdx.x;
+  const size_t tiles = (t.n + TP - 1) / TP;
+  const size_t planes_b = t.rots_before * t.rot_len_before;
+  const size_t planes_all = planes_b + t.rots_after * t.rot_len_after;
+  int levels = 0;
+  while (((size_t)1 << levels) < dm) levels++;
+
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const size_t p0 = tile * TP;
+    const size_t rows = (t.n - p0 < (size_t)TP) ? t.n - p0 : (size_t)TP;
+    for (int tr = 0; tr < t.tries; tr++) {
+      __syncthreads();
+      // coalesced load of the tile, centred (compute.cl:44-49), stored transposed
+      for (size_t e = tid; e < rows * d; e += TP) {
+        size_t r = e / d, c = e - r * d;
+        V[c * LD + r] = points[p0 * d + e] - mean[c];
+      }
+      __syncthreads();
+      if ((size_t)tid < rows) {
+        const u32 *pidx = t.plane_idx + (size_t)tr * planes_all * 2;
+        const FT *pcs = t.plane_cs + (size_t)tr * planes_all * 2;
+        const u32 *permb = t.perm_b + (size_t)tr * dm;
+        const u32 *pick = t.pick + (size_t)tr * t.d_short;
+        // "before" Givens sweeps on the d-vector (compute.cl:55-68)
+        for (size_t q = 0; q < planes_b; q++) {
+          u32 i = pidx[2 * q], j = pidx[2 * q + 1];
+          FT c = pcs[2 * q], s = pcs[2 * q + 1];
+          FT a = V[i * LD + tid], b = V[j * LD + tid];
+          V[i * LD + tid] = a * c - b * s;
+          V[j * LD + tid] = a * s + b * c;
+        }
+        // embed through the sub-permutation (compute.cl:77-85) fused with butterfly level 0
+        if (dm == 1) {
+          Z[tid] = permb[0] < d ? V[permb[0] * LD + tid] : (FT)0;
+        } else {
+          const bool odd = levels & 1;
+          for (size_t y = 0; y < dm; y += 2) {
+            u32 pa = permb[y], pb = permb[y + 1];
+            FT a = pa < d ? V[pa * LD + tid] : (FT)0;
+            FT b = pb < d ? V[pb * LD + tid] : (FT)0;
+            FT lo = a + b, hi = a - b;
+            if (odd) { lo *= t.inv_sqrt2; hi *= t.inv_sqrt2; }   // compute.cl:117-121
+            Z[y * LD + tid] = lo;
+            Z[(y + 1) * LD + tid] = hi;
+          }
+          // remaining butterfly levels; halve on odd levels (compute.cl:107-116)
+          for (int lev = 1; lev < levels; lev++) {
+            const size_t stride = (size_t)1 << lev;
+            const bool halve = lev & 1;
+            for (size_t w = 0; w < dm / 2; w++) {
+              size_t hi_part = (w >> lev) << lev, lo_part = w ^ hi_part;
+              size_t ia = (hi_part << 1) | lo_part, ib = ia | stride;
+              FT a = Z[ia * LD + tid], b = Z[ib * LD + tid];
+              FT s = a + b, df = a - b;
+              if (halve) { s *= (FT)0.5; df *= (FT)0.5; }
+              Z[ia * LD + tid] = s;
+              Z[ib * LD + tid] = df;
+            }
+          }
+        }
+        // "after" sweeps on the first d_short coordinates of the d_max-vector
+        for (size_t q = planes_b; q < planes_all; q++) {
+          u32 i = pidx[2 * q], j = pidx[2 * q + 1];
+          FT c = pcs[2 * q], s = pcs[2 * q + 1];
+          FT a = Z[i * LD + tid], b = Z[j * LD + tid];
+          Z[i * LD + tid] = a * c - b * s;
+          Z[j * LD + tid] = a * s + b * c;
+        }
+        // projection + sign bits, first hashed coordinate = most significant bit
+        u32 h = 0;
+        for (size_t i = 0; i < t.d_short; i++) h = (h << 1) | sign_bit(Z[pick[i] * LD + tid]);
+        hash[(size_t)tr * t.n + p0 + tid] = h;
+      }
+    }
+  }
+}
+
+static const int HASH_TP = 128;
+static const size_t HASH_SMEM_LIMIT = 200 * 1024;
+static const unsigned HASH_SCRATCH_GRID = 148 * 4;
+
+static size_t hash_plane_bytes(const annb_transform_desc *t) {
+  return (t->d + t->d_max) * (size_t)(HASH_TP + 1) * sizeof(FT);
+}
+
+extern "C" size_t annb_hash_scratch_bytes(const annb_transform_desc *t) {
+  size_t need = hash_plane_bytes(t);
+  return need <= HASH_SMEM_LIMIT ? 0 : need * HASH_SCRATCH_GRID;
+}
+
+extern "C" void annb_hash_points(const FT *points, const FT *mean, const annb_transform_desc *t,
+                                 u32 *hash, void *scratch, annb_stream stream) {
+  size_t tiles = (t->n + HASH_TP - 1) / HASH_TP;
+  size_t need = hash_plane_bytes(t);
+  if (need <= HASH_SMEM_LIMIT) {
+    static size_t configured = 0;
+    if (need > configured) {
+      cudaFuncSetAttribute(hash_points_kernel<HASH_TP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)HASH_SMEM_LIMIT);
+      configured = HASH_SMEM_LIMIT;
+    }
+    unsigned grid = (unsigned)(tiles < 148 * 16 ? tiles : 148 * 16);
+    hash_points_kernel<HASH_TP><<<grid, HASH_TP, need, stream>>>(points, mean, *t, hash, nullptr);
+  } else {
+    unsigned grid = (unsigned)(tiles < HASH_SCRATCH_GRID ? tiles : HASH_SCRATCH_GRID);
+    hash_points_kernel<HASH_TP><<<grid, HASH_TP, 0, stream>>>(points, mean, *t, hash, (FT *)scratch);
+  }
+  LAUNCH_CHECK("hash_points");
+}
+
+// =====================================================================================
+// S2: bucket tables
+// =====================================================================================
+
+__global__ void histogram_kernel(const u32 *__restrict__ hash, size_t n, u32 *count) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) atomicAdd(&count[hash[p]], 1u);
+}
+
+// Exclusive scan in three steps: per-block scan (+ block maximum for tmax), scan of the
+// block totals by one CTA, and the add-back.  SCAN_ITEMS counts per block.
+static const int SCAN_THREADS = 256;
+static const int SCAN_PER_THREAD = 8;
+static const int SCAN_ITEMS = SCAN_THREADS * SCAN_PER_THREAD;
+
+__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *total, u32 *warp_sums) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u32 inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    u32 up = __shfl_up_sync(FULL, inc, o);
+    if (lane >= o) inc += up;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    u32 w = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+    u32 winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      u32 up = __shfl_up_sync(FULL, winc, o);
+      if (lane >= o) winc += up;
+    }
+    warp_sums[lane] = winc - w;                 // exclusive warp offsets
+    if (lane == 31) *total = winc;
+  }
+  __syncthreads();
+  u32 res = warp_sums[warp] + inc - v;
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_blocks_kernel(const u32 *__restrict__ count, size_t buckets, u32 *offset, u32 *block_tot,
+                   u32 *tmax) {
+  __shared__ u32 warp_sums[32];
+  __shared__ u32 total;
+  size_t base = (size_t)blockIdx.x * SCAN_ITEMS + (size_t)threadIdx.x * SCAN_PER_THREAD;
+  u32 v[SCAN_PER_THREAD], sum = 0, mx = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_PER_THREAD; i++) {
+    v[i] = base + i < buckets ? count[base + i] : 0;
+    sum += v[i];
+    mx = max(mx, v[i]);
+  }
+  u32 ex = block_exclusive_scan(sum, &total, warp_sums);
+#pragma unroll
+  for (int i = 0; i < SCAN_PER_THREAD; i++) {
+    if (base + i < buckets) offset[base + i] = ex;
+    ex += v[i];
+  }
+  mx = __reduce_max_sync(FULL, mx);
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(tmax, mx);
+  if (threadIdx.x == 0) block_tot[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) scan_totals_kernel(u32 *block_tot, size_t blocks) {
+  __shared__ u32 warp_sums[32];
+  __shared__ u32 total;
+  u32 carry = 0;
+  for (size_t base = 0; base < blocks; base += blockDim.x) {
+    size_t i = base + threadIdx.x;
+    u32 v = i < blocks ? block_tot[i] : 0;
+    u32 ex = block_exclusive_scan(v, &total, warp_sums);
+    if (i < blocks) block_tot[i] = ex + carry;
+    carry += total;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_addback_kernel(u32 *offset, size_t buckets, const u32 *__restrict__ block_tot, u32 n) {
+  size_t base = (size_t)blockIdx.x * SCAN_ITEMS + (size_t)threadIdx.x * SCAN_PER_THREAD;
+  u32 add = block_tot[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_PER_THREAD; i++)
+    if (base + i < buckets) offset[base + i] += add;
+  if (blockIdx.x == 0 && threadIdx.x == 0) offset[buckets] = n;
+}
+
+// Any order inside the bucket; sort_buckets_kernel fixes it.  Consumes `count` (ends at 0).
+__global__ void scatter_kernel(const u32 *__restrict__ hash, size_t n,
+                               const u32 *__restrict__ offset, u32 *count, u32 *order_tmp) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  u32 h = hash[p];
+  u32 slot = atomicSub(&count[h], 1u) - 1u;
+  order_tmp[offset[h] + slot] = (u32)p;
+}
+
+// One warp per bucket: rank every id by the number of larger ids in the bucket, i.e. write
+// the bucket in DEcreasing id order (the reference fills its rows back to front while
+// scanning ids upwards, alg.c:265-266).
+__global__ void sort_buckets_kernel(const u32 *__restrict__ order_tmp,
+                                    const u32 *__restrict__ offset, size_t buckets, u32 *order) {
+  size_t b = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= buckets) return;
+  const int lane = threadIdx.x & 31;
+  u32 beg = offset[b], cnt = offset[b + 1] - beg;
+  if (cnt <= 32) {
+    u32 mine = lane < (int)cnt ? order_tmp[beg + lane] : 0;
+    u32 rank = 0;
+    for (u32 j = 0; j < cnt; j++) {
+      u32 other = __shfl_sync(FULL, mine, j);
+      rank += other > mine;
+    }
+    if (lane < (int)cnt) order[beg + rank] = mine;
+  } else {
+    for (u32 e = lane; e < cnt; e += 32) {
+      u32 mine = order_tmp[beg + e], rank = 0;
+      for (u32 j = 0; j < cnt; j++) rank += order_tmp[beg + j] > mine;
+      order[beg + rank] = mine;
+    }
+  }
+}
+
+extern "C" size_t annb_scan_tmp_bytes(size_t buckets) {
+  size_t blocks = (buckets + SCAN_ITEMS - 1) / SCAN_ITEMS;
+  return (blocks + 1) * sizeof(u32);
+}
+
+extern "C" void annb_build_buckets(const u32 *hash, size_t n, size_t buckets, u32 *count,
+                                   u32 *offset, u32 *order_tmp, u32 *order, u32 *tmax,
+                                   void *scan_tmp, annb_stream stream) {
+  u32 *block_tot = (u32 *)scan_tmp;
+  size_t blocks = (buckets + SCAN_ITEMS - 1) / SCAN_ITEMS;
+  cudaMemsetAsync(count, 0, buckets * sizeof(u32), stream);
+  cudaMemsetAsync(tmax, 0, sizeof(u32), stream);
+  histogram_kernel<<<grid_for(n, 256), 256, 0, stream>>>(hash, n, count);
+  LAUNCH_CHECK("histogram");
+  scan_blocks_kernel<<<(unsigned)blocks, SCAN_THREADS, 0, stream>>>(count, buckets, offset, block_tot, tmax);
+  LAUNCH_CHECK("scan_blocks");
+  scan_totals_kernel<<<1, 1024, 0, stream>>>(block_tot, blocks);
+  LAUNCH_CHECK("scan_totals");
+  scan_addback_kernel<<<(unsigned)blocks, SCAN_THREADS, 0, stream>>>(offset, buckets, block_tot, (u32)n);
+  LAUNCH_CHECK("scan_addback");
+  scatter_kernel<<<grid_for(n, 256), 256, 0, stream>>>(hash, n, offset, count, order_tmp);
+  LAUNCH_CHECK("scatter");
+  sort_buckets_kernel<<<grid_for(buckets * 32, 256), 256, 0, stream>>>(order_tmp, offset, buckets, order);
+  LAUNCH_CHECK("sort_buckets");
+}
+
+// sorted_points[r] = points[order[r]]: a group of lanes per row, 16-byte pieces when rows allow
+template <typename VEC>
+__global__ void gather_rows_kernel(const VEC *__restrict__ src, const u32 *__restrict__ order,
+                                   size_t n, u32 vec_per_row, u32 lanes_per_row, VEC *dst) {
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t r = gid / lanes_per_row;
+  u32 sub = (u32)(gid - r * lanes_per_row);
+  if (r >= n) return;
+  const VEC *s = src + (size_t)order[r] * vec_per_row;
+  VEC *o = dst + r * vec_per_row;
+  for (u32 v = sub; v < vec_per_row; v += lanes_per_row) o[v] = s[v];
+}
+
+extern "C" void annb_gather_rows(const FT *points, const u32 *order, size_t n, size_t d,
+                                 FT *sorted_points, annb_stream stream) {
+  size_t row_bytes = d * sizeof(FT);
+  if (row_bytes % 16 == 0) {
+    u32 vpr = (u32)(row_bytes / 16);
+    u32 lanes = 1;
+    while (lanes < vpr && lanes < 32) lanes <<= 1;
+    gather_rows_kernel<uint4><<<grid_for(n * lanes, 256), 256, 0, stream>>>(
+        (const uint4 *)points, order, n, vpr, lanes, (uint4 *)sorted_points);
+  } else {
+    u32 vpr = (u32)(row_bytes / 4);
+    u32 lanes = 1;
+    while (lanes < vpr && lanes < 32) lanes <<= 1;
+    gather_rows_kernel<u32><<<grid_for(n * lanes, 256), 256, 0, stream>>>(
+        (const u32 *)points, order, n, vpr, lanes, (u32 *)sorted_points);
+  }
+  LAUNCH_CHECK("gather_rows");
+}
+
+__global__ void export_table_kernel(const u32 *__restrict__ offset, const u32 *__restrict__ order,
+                                    size_t n, size_t buckets, size_t tmax, size_t *table) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= buckets * tmax) return;
+  size_t b = e / tmax, z = e - b * tmax;
+  u32 beg = offset[b], cnt = offset[b + 1] - beg;
+  table[e] = z < cnt ? (size_t)order[beg + z] : n;
+}
+
+extern "C" void annb_export_table(const u32 *offset, const u32 *order, size_t n, size_t buckets,
+                                  size_t tmax, size_t *table, annb_stream stream) {
+  export_table_kernel<<<grid_for(buckets * tmax, 256), 256, 0, stream>>>(offset, order, n, buckets, tmax, table);
+  LAUNCH_CHECK("export_table");
+}
+

@@ -75,17 +75,27 @@ void annb_gather_rows(const ftype *points, const annb_u32 *order, size_t n, size
 void annb_export_table(const annb_u32 *offset, const annb_u32 *order, size_t n, size_t buckets,
                        size_t tmax, size_t *table, annb_stream stream);
 
+/* ---- exact ties ------------------------------------------------------------------------
+ * S3, S4 and S5 each run a fast kernel that keeps the k best per row, then redo — with the
+ * reference's literal row and sorting network — the rare rows in which two DIFFERENT ids
+ * at exactly the same distance could influence the result (the reference's output then
+ * depends on where its network leaves equal keys, and it can even keep an id twice).
+ * `scratch` holds the per-row flags and the literal rows; *status (device int) is set to 1
+ * if the scratch was too small for even one literal row.                                  */
+
 /* ---- S3: candidate distances + per-point k best of one try ----------------------------
  * Replaces compute_which, compute_diffs_squared, add_cols_step, sort_two_step, rdups for
  * the per-try rows (compute.cl:135-217,238-246; alg.c:274-288).  A point's candidates
  * are the slots p < P of the virtual row [bucket h, h^1, h^2, h^4, ...] (tmax slots each),
  * P = 2^floor(log2((d_short+1)*tmax)) — the reference's prefix rule (SURVEY §8.A.3 rule 5).
  * list_ids/list_dist: [n][k], ascending squared distance, (n, +inf) where fewer than k
- * finite candidates exist.  `tmax` is read on the device.                                 */
+ * finite candidates exist.  `tmax` is read on the device.
+ * scratch: annb_leaf_scratch_bytes(n) bytes.                                               */
+size_t annb_leaf_scratch_bytes(size_t n);
 void annb_leaf_topk(const ftype *sorted_points, const annb_u32 *order, const annb_u32 *offset,
                     const annb_u32 *hash, const annb_u32 *tmax, size_t n, size_t d,
                     size_t d_short, size_t k, annb_u32 *list_ids, ftype *list_dist,
-                    annb_stream stream);
+                    void *scratch, int *status, annb_stream stream);
 
 /* ---- S4: merge of the per-try lists (first sort_and_uniq of det_results, alg.c:312) ----
  * lists: [n_lists][n][k]; admit[i] = number of leading entries of list i that fall inside
@@ -93,35 +103,27 @@ void annb_leaf_topk(const ftype *sorted_points, const annb_u32 *order, const ann
  * corner_list/corner_pos: the list entry sitting in the first slot OUTSIDE the prefix
  * (or corner_list < 0 when the row length is a power of two) — see DESIGN.md "prefix
  * corner".  merged: [n][k].  If merged_in != NULL it is treated as one more, fully
- * admitted list (running merge).                                                          */
+ * admitted list (running merge; no literal redo is possible then).  Rows shorter than 16
+ * slots (k*n_lists < 16) are always done literally.
+ * scratch: at least n + 512 bytes plus room for literal rows (64 MB is plenty).           */
 void annb_merge_lists(const annb_u32 *lists_ids, const ftype *lists_dist, int n_lists,
                       const int *host_admit, int corner_list, int corner_pos,
                       const annb_u32 *merged_in_ids, const ftype *merged_in_dist,
                       size_t n, size_t k, annb_u32 *merged_ids, ftype *merged_dist,
-                      annb_stream stream);
+                      void *scratch, size_t scratch_bytes, int *status, annb_stream stream);
 
 /* ---- S5: supercharging (supercharge + compdists + second sort_and_uniq, alg.c:313-335) --
  * For each query row x in [row_begin, row_end): candidates = own list ++ the lists of its
  * neighbours (graph rows), prefix 2^floor(log2(k(k+1))); distances from queries[x] to
  * points[id]; out rows are relative to row_begin.  exclude_self: the reference excludes
  * id == x only when the query set IS the point set (compute.cl:145).
- * graph may be the merged ids themselves (precomp) or save->graph (query).                */
+ * graph may be the merged ids themselves (precomp) or save->graph (query).
+ * scratch: at least (row_end-row_begin) + 512 bytes plus room for literal rows.           */
 void annb_supercharge(const ftype *queries, const ftype *points, const annb_u32 *own_ids,
                       const ftype *own_dist, const annb_u32 *graph, size_t n, size_t d,
                       size_t k, size_t row_begin, size_t row_end, int exclude_self,
-                      size_t *out_ids, ftype *out_dist, annb_stream stream);
-
-/* ---- literal fall-back for rows shorter than 16 slots ---------------------------------
- * The reference's sort degenerates to independent blocks when a row has fewer than 16
- * slots (k*tries < 16 or k(k+1) < 16; SURVEY §8.A.3 rule 5).  These two emulate the
- * network literally, one thread per row.                                                  */
-void annb_merge_lists_tiny(const annb_u32 *lists_ids, const ftype *lists_dist, int n_lists,
-                           size_t n, size_t k, annb_u32 *merged_ids, ftype *merged_dist,
-                           annb_stream stream);
-void annb_supercharge_tiny(const ftype *queries, const ftype *points, const annb_u32 *own_ids,
-                           const ftype *own_dist, const annb_u32 *graph, size_t n, size_t d,
-                           size_t k, size_t row_begin, size_t row_end, int exclude_self,
-                           size_t *out_ids, ftype *out_dist, annb_stream stream);
+                      size_t *out_ids, ftype *out_dist, void *scratch, size_t scratch_bytes,
+                      int *status, annb_stream stream);
 
 /* number of kernels launched through this layer since the last reset (bench.py reports it) */
 unsigned long annb_launch_count(int reset);
