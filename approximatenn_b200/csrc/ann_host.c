@@ -94,6 +94,7 @@ void gpu_cleanup(void) {
     free(h);
   }
   CK(cudaStreamSynchronize(G.stream));
+  annh_egress_release();
   if (G.arena) CK(cudaFree(G.arena));
   G.arena = NULL;
   G.arena_bytes = G.arena_used = 0;
@@ -298,6 +299,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   const size_t T = (size_t)tries, buckets = (size_t)1 << d_short;
   const size_t planes = rots_before * rot_len_before + rots_after * rot_len_after;
   cudaStream_t st = G.stream;
+  annh_egress *eg = annh_egress_begin(n, k, dists_o != NULL, G.device);
 
   /* 1. transforms: ALL tries are drawn before any compute (alg.c:388-392)              */
   host_transform *tf = malloc(sizeof(host_transform) * T);
@@ -340,7 +342,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
                  pad256(T * planes * 2 * 4 + 4) + pad256(T * planes * 2 * w + w) +
                  pad256(T * d_max * 4) + pad256(T * d_short * 4 + 4) +
                  pad256(annb_hash_scratch_bytes(&desc)) +
-                 pad256(n * k * 4) * 2 + pad256(n * k * w) * 3 + pad256(n * k * sizeof(size_t)) +
+                 pad256(n * k * 4) * 3 + pad256(n * k * w) * 3 +
                  pad256(annb_leaf_scratch_bytes(n)) + 8192;
   size_t group = T;                                            /* lists kept before a merge */
   while (group > 1 && fixed + group * list_bytes + 512 > free_b * 9 / 10) group--;
@@ -361,7 +363,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   ftype *dl_dist = arena_take(group * n * k * w);
   annb_u32 *dm_ids = arena_take(n * k * 4), *dm_ids2 = arena_take(n * k * 4);
   ftype *dm_dist = arena_take(n * k * w), *dm_dist2 = arena_take(n * k * w);
-  size_t *dout_ids = arena_take(n * k * sizeof(size_t));
+  annb_u32 *dout_ids = arena_take(n * k * 4);
   ftype *dout_dist = arena_take(n * k * w);
   const size_t scratch_bytes = annb_leaf_scratch_bytes(n);
   void *dscratch = arena_take(scratch_bytes);
@@ -457,17 +459,18 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   mark(5);
 
   /* 7. S5 supercharging (alg.c:313-327); the graph is the merged lists themselves        */
-  annb_supercharge(dX, dX, dm_ids, dm_dist, dm_ids, n, d, k, 0, n, 1, dout_ids,
-                   dists_o ? dout_dist : NULL, dscratch, scratch_bytes, dstatus, st);
+  {
+    int nch = annh_egress_chunks(eg);
+    for (int c = 0; c < nch; c++) {
+      size_t r0 = (n * (size_t)c / nch) & ~(size_t)31, r1 = c + 1 == nch ? n : (n * (size_t)(c + 1) / nch) & ~(size_t)31;
+      annb_supercharge(dX, dX, dm_ids, dm_dist, dm_ids, n, d, k, r0, r1, 1, dout_ids + r0 * k,
+                       dists_o ? dout_dist + r0 * k : NULL, dscratch, scratch_bytes, dstatus, st);
+      annh_egress_chunk(eg, r0, r1, dout_ids + r0 * k, dout_dist + r0 * k, st);
+    }
+  }
   mark(6);
 
-  /* 8. results                                                                          */
-  size_t *result = malloc(sizeof(size_t) * n * k);
-  CK(cudaMemcpyAsync(result, dout_ids, sizeof(size_t) * n * k, cudaMemcpyDeviceToHost, st));
-  if (dists_o) {
-    *dists_o = malloc(w * n * k);
-    CK(cudaMemcpyAsync(*dists_o, dout_dist, w * n * k, cudaMemcpyDeviceToHost, st));
-  }
+  /* 8. results: the egress threads are already widening the first chunks                 */
   annb_u32 *h_tmax = malloc(4 * T);
   int h_status = 0;
   CK(cudaMemcpyAsync(h_tmax, dtmax, 4 * T, cudaMemcpyDeviceToHost, st));
@@ -475,6 +478,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   mark(7);
   CK(cudaStreamSynchronize(st));
   collect_times();
+  size_t *result = annh_egress_end(eg, dists_o);
   if (h_status) annh_fatal("%s", "scratch too small for a literal candidate row (extremely unbalanced buckets)");
   for (size_t t = 0; t < T; t++)
     if ((d_short + 1) * (size_t)h_tmax[t] < 16)

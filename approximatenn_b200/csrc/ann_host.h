@@ -27,6 +27,16 @@ typedef struct { float ms[ANNH_STAGES]; } annh_stage_times;
 const annh_stage_times *annh_last_times(void);
 void annh_set_timing(int on);
 
+/* result egress (ann_results.c): malloc()ed result arrays filled chunk by chunk through a
+ * pinned staging buffer while later chunks are still being computed                        */
+typedef struct annh_egress annh_egress;
+annh_egress *annh_egress_begin(size_t rows, size_t k, int want_dist, int device);
+int annh_egress_chunks(const annh_egress *e);          /* how many row chunks to produce    */
+void annh_egress_chunk(annh_egress *e, size_t r0, size_t r1, const void *dev_ids_u32,
+                       const void *dev_dist, void *producer_stream);
+size_t *annh_egress_end(annh_egress *e, ftype **dists_o);
+void annh_egress_release(void);
+
 /* drops any device-resident copy of `save` kept for query_gpu (called by free_save)      */
 void annh_forget_save(const save_t *save);
 

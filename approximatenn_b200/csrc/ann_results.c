@@ -1,0 +1,187 @@
+/* ann_results.c — egress of result rows: device (u32 ids, ftype distances) -> the
+ * malloc()ed size_t / ftype arrays the API returns (ann.h).
+ *
+ * A fresh malloc of this size is an mmap of untouched pages; copying straight into it
+ * page-faults every 4 KB and costs more than the whole GPU computation, and page-locking
+ * it (cudaHostRegister) is no cheaper.  So:
+ *   - the arrays are allocated before the GPU starts and a few host threads touch their
+ *     pages while the GPU works;
+ *   - result rows leave the device in chunks as soon as the last stage has produced them:
+ *     a copy stream moves each chunk (ids still 32-bit) into a cached pinned staging
+ *     buffer, and the same host threads widen the ids to size_t and copy the distances
+ *     into the caller-visible arrays while later chunks are still being computed.
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include <cuda_runtime_api.h>
+
+#include "ann_host.h"
+#include "annb200.h"
+
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      fprintf(stderr, "approximatenn_b200: %s failed at %s:%d: %s\n", #call, __FILE__,  \
+              __LINE__, cudaGetErrorString(e_));                                        \
+      exit(1);                                                                          \
+    }                                                                                   \
+  } while (0)
+
+#define EGRESS_MAX_CHUNKS 64
+#define EGRESS_MAX_THREADS 16
+
+typedef struct { size_t r0, r1; cudaEvent_t done; } egress_chunk;
+
+struct annh_egress {
+  size_t rows, k;
+  size_t *ids;            /* [rows][k] result, caller-owned after end()        */
+  ftype *dist;            /* [rows][k] or NULL                                 */
+  annb_u32 *stage_ids;    /* pinned staging (cached in S)                      */
+  ftype *stage_dist;
+  int device, nthreads;
+  pthread_t th[EGRESS_MAX_THREADS];
+  struct { struct annh_egress *e; int idx; } arg[EGRESS_MAX_THREADS];
+  pthread_mutex_t mu;
+  pthread_cond_t cv;
+  int submitted, closed;
+  egress_chunk chunk[EGRESS_MAX_CHUNKS];
+};
+
+static struct {
+  void *stage;
+  size_t stage_bytes;
+  cudaStream_t copy;
+  cudaEvent_t produced;
+  int ready;
+} S;
+
+void annh_egress_release(void) {
+  if (S.stage) CK(cudaFreeHost(S.stage));
+  S.stage = NULL;
+  S.stage_bytes = 0;
+  if (S.ready) {
+    CK(cudaEventDestroy(S.produced));
+    CK(cudaStreamDestroy(S.copy));
+    S.ready = 0;
+  }
+}
+
+static void *egress_worker(void *p) {
+  struct annh_egress *e = ((struct { struct annh_egress *e; int idx; } *)p)->e;
+  const int me = ((struct { struct annh_egress *e; int idx; } *)p)->idx;
+  cudaSetDevice(e->device);
+  /* 1. fault in this thread's share of the result pages while the GPU computes          */
+  {
+    size_t cells = e->rows * e->k;
+    size_t lo = cells * (size_t)me / e->nthreads, hi = cells * (size_t)(me + 1) / e->nthreads;
+    volatile char *a = (volatile char *)(e->ids + lo);
+    for (size_t o = 0; o < (hi - lo) * sizeof(size_t); o += 4096) a[o] = 0;
+    if (hi > lo) a[(hi - lo) * sizeof(size_t) - 1] = 0;
+    if (e->dist) {
+      volatile char *b = (volatile char *)(e->dist + lo);
+      for (size_t o = 0; o < (hi - lo) * sizeof(ftype); o += 4096) b[o] = 0;
+      if (hi > lo) b[(hi - lo) * sizeof(ftype) - 1] = 0;
+    }
+  }
+  /* 2. chunks me, me+nthreads, ...: wait for the copy stream, widen ids, copy distances */
+  for (int c = me;; c += e->nthreads) {
+    pthread_mutex_lock(&e->mu);
+    while (c >= e->submitted && !e->closed) pthread_cond_wait(&e->cv, &e->mu);
+    int have = c < e->submitted;
+    pthread_mutex_unlock(&e->mu);
+    if (!have) break;
+    egress_chunk *ch = &e->chunk[c];
+    if (cudaEventSynchronize(ch->done) != cudaSuccess) {
+      fprintf(stderr, "approximatenn_b200: result copy failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+      exit(1);
+    }
+    size_t lo = ch->r0 * e->k, hi = ch->r1 * e->k;
+    const annb_u32 *src = e->stage_ids;
+    size_t *dst = e->ids;
+    for (size_t i = lo; i < hi; i++) dst[i] = src[i];
+    if (e->dist) memcpy(e->dist + lo, e->stage_dist + lo, (hi - lo) * sizeof(ftype));
+  }
+  return NULL;
+}
+
+annh_egress *annh_egress_begin(size_t rows, size_t k, int want_dist, int device) {
+  annh_egress *e = calloc(1, sizeof *e);
+  e->rows = rows; e->k = k; e->device = device;
+  e->ids = malloc(sizeof(size_t) * rows * k);
+  e->dist = want_dist ? malloc(sizeof(ftype) * rows * k) : NULL;
+  if (!e->ids || (want_dist && !e->dist)) annh_fatal("%s", "out of host memory for the result arrays");
+  if (!S.ready) {
+    CK(cudaStreamCreateWithFlags(&S.copy, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&S.produced, cudaEventDisableTiming));
+    S.ready = 1;
+  }
+  size_t need = rows * k * (sizeof(annb_u32) + sizeof(ftype)) + 256;
+  if (need > S.stage_bytes) {
+    if (S.stage) CK(cudaFreeHost(S.stage));
+    CK(cudaMallocHost(&S.stage, need));
+    S.stage_bytes = need;
+  }
+  e->stage_dist = (ftype *)S.stage;                                   /* 8-byte aligned first */
+  e->stage_ids = (annb_u32 *)((char *)S.stage + ((rows * k * sizeof(ftype) + 255) & ~(size_t)255));
+  pthread_mutex_init(&e->mu, NULL);
+  pthread_cond_init(&e->cv, NULL);
+  int nt = 4;
+  const char *env = getenv("ANN_B200_HOST_THREADS");
+  if (env && *env) nt = atoi(env);
+  long cores = sysconf(_SC_NPROCESSORS_ONLN);
+  if (cores > 1 && nt > cores - 1) nt = (int)cores - 1;
+  if (rows * k < ((size_t)1 << 18)) nt = 1;
+  if (nt < 1) nt = 1;
+  if (nt > EGRESS_MAX_THREADS) nt = EGRESS_MAX_THREADS;
+  e->nthreads = nt;
+  for (int i = 0; i < nt; i++) {
+    e->arg[i].e = e;
+    e->arg[i].idx = i;
+    if (pthread_create(&e->th[i], NULL, egress_worker, &e->arg[i]) != 0)
+      annh_fatal("%s", "pthread_create failed");
+  }
+  return e;
+}
+
+int annh_egress_chunks(const annh_egress *e) {
+  return e->rows >= ((size_t)1 << 17) ? 8 : 1;
+}
+
+void annh_egress_chunk(annh_egress *e, size_t r0, size_t r1, const void *dev_ids,
+                       const void *dev_dist, void *producer_stream) {
+  if (e->submitted >= EGRESS_MAX_CHUNKS) annh_fatal("%s", "internal: too many egress chunks");
+  egress_chunk *ch = &e->chunk[e->submitted];
+  ch->r0 = r0; ch->r1 = r1;
+  CK(cudaEventCreateWithFlags(&ch->done, cudaEventDisableTiming | cudaEventBlockingSync));
+  CK(cudaEventRecord(S.produced, (cudaStream_t)producer_stream));
+  CK(cudaStreamWaitEvent(S.copy, S.produced, 0));
+  size_t cells = (r1 - r0) * e->k;
+  CK(cudaMemcpyAsync(e->stage_ids + r0 * e->k, dev_ids, cells * sizeof(annb_u32), cudaMemcpyDeviceToHost, S.copy));
+  if (e->dist)
+    CK(cudaMemcpyAsync(e->stage_dist + r0 * e->k, dev_dist, cells * sizeof(ftype), cudaMemcpyDeviceToHost, S.copy));
+  CK(cudaEventRecord(ch->done, S.copy));
+  pthread_mutex_lock(&e->mu);
+  e->submitted++;
+  pthread_cond_broadcast(&e->cv);
+  pthread_mutex_unlock(&e->mu);
+}
+
+size_t *annh_egress_end(annh_egress *e, ftype **dists_o) {
+  pthread_mutex_lock(&e->mu);
+  e->closed = 1;
+  pthread_cond_broadcast(&e->cv);
+  pthread_mutex_unlock(&e->mu);
+  for (int i = 0; i < e->nthreads; i++) pthread_join(e->th[i], NULL);
+  for (int c = 0; c < e->submitted; c++) CK(cudaEventDestroy(e->chunk[c].done));
+  pthread_mutex_destroy(&e->mu);
+  pthread_cond_destroy(&e->cv);
+  size_t *ids = e->ids;
+  if (dists_o) *dists_o = e->dist;
+  free(e);
+  return ids;
+}

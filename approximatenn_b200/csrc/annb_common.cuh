@@ -152,7 +152,7 @@ struct WarpList {
   __device__ __forceinline__ bool contains(u32 key) const {
     bool f = false;
 #pragma unroll
-    for (int r = 0; r < R; r++) f |= (id[r] == key);
+    for (int r = 0; r < R; r++) f |= (id[r] == key && v[r] != ft_inf());
     return __any_sync(FULL, f);
   }
   // (vn, idn) warp-uniform, vn < kth(k), idn not contained

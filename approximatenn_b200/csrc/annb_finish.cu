@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256)
 supercharge_kernel(const FT *__restrict__ queries, const FT *__restrict__ points,
                    const u32 *__restrict__ own_ids, const FT *__restrict__ own_dist,
                    const u32 *__restrict__ graph, size_t n, int d, int k, size_t row_begin,
-                   size_t row_end, int exclude_self, size_t *__restrict__ out_ids,
+                   size_t row_end, int exclude_self, u32 *__restrict__ out_ids,
                    FT *__restrict__ out_dist, unsigned char *__restrict__ tie_flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -253,11 +253,154 @@ supercharge_kernel(const FT *__restrict__ queries, const FT *__restrict__ points
   for (int rr = 0; rr < R; rr++) {
     int p = rr * 32 + lane;
     if (p < k) {
-      out_ids[orow * (size_t)k + p] = (size_t)best.id[rr];
+      out_ids[orow * (size_t)k + p] = best.id[rr];
       if (out_dist) out_dist[orow * (size_t)k + p] = best.v[rr];
     }
   }
   if (tie && tie_flags && lane == 0) tie_flags[orow] = 1;
+}
+
+// ---- fast path (k <= 32, d in {16,32,64,128}) -------------------------------------------
+// Neighbour-of-neighbour lists repeat the same ids many times, and equal ids have equal
+// distances, so the candidate ids of a row are de-duplicated FIRST (a per-warp hash set in
+// shared memory, seeded with the own list) and only the distinct ones are gathered.  Four
+// candidates are measured per step: 8 lanes per candidate, lane g holding coordinates
+// g, g+8, g+16, ... so that the first levels of the reference's summation tree are
+// lane-local and the last three are xor-shuffles inside the 8-lane group.
+#define HS_EMPTY 0xffffffffu
+
+__device__ __forceinline__ bool hs_insert(u32 *tab, u32 mask, int shift, u32 id) {
+  u32 h = (id * 2654435761u) >> shift;
+  while (true) {
+    u32 old = atomicCAS(&tab[h], HS_EMPTY, id);
+    if (old == HS_EMPTY) return true;
+    if (old == id) return false;
+    h = (h + 1) & mask;
+  }
+}
+
+template <int EPL>
+__global__ void __launch_bounds__(256)
+supercharge_fast_kernel(const FT *__restrict__ queries, const FT *__restrict__ points,
+                        const u32 *__restrict__ own_ids, const FT *__restrict__ own_dist,
+                        const u32 *__restrict__ graph, size_t n, int k, size_t row_begin,
+                        size_t row_end, int exclude_self, int table_log2,
+                        u32 *__restrict__ out_ids, FT *__restrict__ out_dist,
+                        unsigned char *__restrict__ tie_flags) {
+  constexpr int D = EPL * 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  size_t x = row_begin + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (x >= row_end) return;
+  const u32 sentinel = (u32)n;
+  const int wide = k * (k + 1);
+  const int P2 = 1 << floor_log2_u((unsigned long long)wide);
+  const int cand = P2 - k;
+  const u32 tsize = 1u << table_log2, tmask = tsize - 1;
+  const int shift = 32 - table_log2;
+  u32 *tab = reinterpret_cast<u32 *>(smem_raw) + (size_t)wib * (tsize + (size_t)k * k);
+  u32 *uniq = tab + tsize;
+
+  for (u32 i = lane; i < tsize; i += 32) tab[i] = HS_EMPTY;
+
+  const int g = lane & 7, grp = lane >> 3;
+  FT q[EPL];
+  {
+    const FT *qrow = queries + x * (size_t)D;
+#pragma unroll
+    for (int s = 0; s < EPL; s++) q[s] = qrow[g + 8 * s];
+  }
+
+  WarpList<1> best;
+  best.v[0] = lane < k ? own_dist[x * (size_t)k + lane] : ft_inf();
+  best.id[0] = lane < k ? own_ids[x * (size_t)k + lane] : sentinel;
+  const u32 own_reg = best.id[0];
+  bool tie = false;
+  bool any_inf = lane < k && best.v[0] == ft_inf();
+  FT max_v = (lane < k && best.v[0] != ft_inf()) ? best.v[0] : -ft_inf();
+  u32 max_id = best.id[0];
+  {
+    FT nxt = __shfl_down_sync(FULL, best.v[0], 1);
+    if (lane + 1 < k && best.v[0] == nxt && nxt != ft_inf()) tie = true;
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    FT ov = __shfl_xor_sync(FULL, max_v, o);
+    u32 oi = __shfl_xor_sync(FULL, max_id, o);
+    if (ov > max_v) { max_v = ov; max_id = oi; }
+  }
+  FT tau = best.kth(k);
+  __syncwarp();
+  // only FINITE own entries stand for their id (an id carried with +inf may come back finite)
+  if (lane < k && own_reg < sentinel && best.v[0] != ft_inf()) hs_insert(tab, tmask, shift, own_reg);
+  if (exclude_self && lane == 0) hs_insert(tab, tmask, shift, (u32)x);
+  __syncwarp();
+
+  // distinct candidate ids -> uniq[0..U)
+  int U = 0;
+  for (int base = 0; base < cand; base += 32) {
+    int c = base + lane;
+    int j = c < cand ? c / k : 0;
+    int z = c - j * k;
+    u32 oj = __shfl_sync(FULL, own_reg, j);
+    u32 cid = (c < cand && oj < sentinel) ? graph[(size_t)oj * k + z] : sentinel;
+    bool keep = false;
+    if (c < cand) {
+      if (cid >= sentinel || (exclude_self && cid == (u32)x)) any_inf = true;
+      else keep = hs_insert(tab, tmask, shift, cid);
+    }
+    unsigned m = __ballot_sync(FULL, keep);
+    if (keep) uniq[U + __popc(m & ((1u << lane) - 1))] = cid;
+    U += __popc(m);
+  }
+  any_inf = __any_sync(FULL, any_inf);
+  tie = __any_sync(FULL, tie);
+  __syncwarp();
+
+  for (int base = 0; base < U; base += 4) {
+    int mine = base + grp;
+    u32 cid = uniq[mine < U ? mine : base];
+    const FT *crow = points + (size_t)cid * D;
+    FT m[EPL];
+#pragma unroll
+    for (int s = 0; s < EPL; s++) {
+      FT df = q[s] - crow[g + 8 * s];
+      m[s] = df * df;
+    }
+#pragma unroll
+    for (int h = EPL / 2; h >= 1; h >>= 1)
+#pragma unroll
+      for (int s = 0; s < h; s++) m[s] = m[s] + m[s + h];
+    FT v = m[0];
+    v = v + __shfl_xor_sync(FULL, v, 4);
+    v = v + __shfl_xor_sync(FULL, v, 2);
+    v = v + __shfl_xor_sync(FULL, v, 1);
+    int cnt = min(4, U - base);
+    for (int i = 0; i < cnt; i++) {
+      FT vn = __shfl_sync(FULL, v, 8 * i);
+      u32 idn = __shfl_sync(FULL, cid, 8 * i);
+      if (vn > max_v) { max_v = vn; max_id = idn; }
+      if (vn < tau) {
+        if (__any_sync(FULL, best.v[0] == vn)) tie = true;
+        best.insert(vn, idn, k, sentinel, lane);
+        tau = best.kth(k);
+      } else if (vn == tau && vn != ft_inf()) {
+        tie = true;
+      }
+    }
+  }
+  if (P2 < wide && !any_inf) {
+    int c = P2 - k, j = c / k, z = c - j * k;
+    u32 oj = __shfl_sync(FULL, own_reg, j);
+    u32 cid = oj < sentinel ? graph[(size_t)oj * k + z] : sentinel;
+    if (cid == max_id) best.remove(cid, sentinel, lane);
+  }
+  size_t orow = x - row_begin;
+  if (lane < k) {
+    out_ids[orow * (size_t)k + lane] = best.id[0];
+    if (out_dist) out_dist[orow * (size_t)k + lane] = best.v[0];
+  }
+  if (tie && lane == 0) tie_flags[orow] = 1;
 }
 
 // Literal row of k(k+1) slots (supercharge + compdists + sort_and_uniq, alg.c:313-327).
@@ -266,7 +409,7 @@ __global__ void __launch_bounds__(256)
 supercharge_literal_kernel(const FT *__restrict__ queries, const FT *__restrict__ points,
                            const u32 *__restrict__ own_ids, const FT *__restrict__ own_dist,
                            const u32 *__restrict__ graph, size_t n, int d, int k, size_t row_begin,
-                           size_t row_end, int exclude_self, size_t *__restrict__ out_ids,
+                           size_t row_end, int exclude_self, u32 *__restrict__ out_ids,
                            FT *__restrict__ out_dist, const unsigned char *__restrict__ tie_flags,
                            unsigned char *scratch, size_t scratch_bytes, int *status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -313,7 +456,7 @@ supercharge_literal_kernel(const FT *__restrict__ queries, const FT *__restrict_
       __syncwarp();
       warp_sort_and_uniq(ids, key, wide, lane);
       for (int i = lane; i < k; i += 32) {
-        out_ids[orow * (size_t)k + i] = (size_t)ids[i];
+        out_ids[orow * (size_t)k + i] = ids[i];
         if (out_dist) out_dist[orow * (size_t)k + i] = key[i];
       }
       __syncwarp();
@@ -325,8 +468,8 @@ template <int E>
 static void launch_supercharge(int regs, size_t smem, annb_stream stream, const FT *queries,
                                const FT *points, const u32 *own_ids, const FT *own_dist,
                                const u32 *graph, size_t n, int d, int k, size_t rb, size_t re, int ex,
-                               size_t *out_ids, FT *out_dist, unsigned char *flags,
-                               unsigned char *slabs, size_t slab_bytes, int *status, bool all_literal) {
+                               u32 *out_ids, FT *out_dist, unsigned char *flags,
+                               unsigned char *slabs, size_t slab_bytes, int *status, bool all_literal, bool skip_main) {
   dim3 block(256), grid(grid_for((re - rb) * 32, 256));
 #define SC_CASE(R)                                                                               \
   {                                                                                              \
@@ -334,7 +477,7 @@ static void launch_supercharge(int regs, size_t smem, annb_stream stream, const 
       cudaFuncSetAttribute(supercharge_kernel<E, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     supercharge_kernel<E, R><<<grid, block, smem, stream>>>(queries, points, own_ids, own_dist, graph, n, d, k, rb, re, ex, out_ids, out_dist, flags); \
   }
-  if (!all_literal) {
+  if (!all_literal && !skip_main) {
     switch (regs) {
       case 1: SC_CASE(1) break;
       case 2: SC_CASE(2) break;
@@ -355,7 +498,7 @@ static void launch_supercharge(int regs, size_t smem, annb_stream stream, const 
 extern "C" void annb_supercharge(const FT *queries, const FT *points, const u32 *own_ids,
                                  const FT *own_dist, const u32 *graph, size_t n, size_t d, size_t k,
                                  size_t row_begin, size_t row_end, int exclude_self,
-                                 size_t *out_ids, FT *out_dist, void *scratch, size_t scratch_bytes,
+                                 u32 *out_ids, FT *out_dist, void *scratch, size_t scratch_bytes,
                                  int *status, annb_stream stream) {
   if (row_end <= row_begin) return;
   int regs = list_regs(k);
@@ -368,8 +511,39 @@ extern "C" void annb_supercharge(const FT *queries, const FT *points, const u32 
   unsigned char *slabs = (unsigned char *)(((uintptr_t)(flags + rows) + 255) & ~(uintptr_t)255);
   size_t slab_bytes = scratch_bytes > rows + 512 ? scratch_bytes - rows - 512 : 0;
   const bool all_literal = k * (k + 1) < 16;      // the network degenerates: literal rows only
+  bool all_literal_redo_only = false;             // fast kernel already ran: only the flagged redo
   if (!all_literal) cudaMemsetAsync(flags, 0, rows, stream);
-#define SC_ARGS regs, smem, stream, queries, points, own_ids, own_dist, graph, n, (int)d, (int)k, row_begin, row_end, exclude_self, out_ids, out_dist, flags, slabs, slab_bytes, status, all_literal
+  // fast path
+  {
+    const char *off = getenv("ANN_B200_NO_FAST_SUPERCHARGE");
+    bool allow = !(off && *off && *off != '0');
+    int epl = (d == 16 || d == 32 || d == 64 || d == 128) ? (int)(d / 8) : 0;
+    if (allow && !all_literal && k <= 32 && epl) {
+      int P2 = 1;
+      while ((size_t)P2 * 2 <= k * (k + 1)) P2 *= 2;
+      int tl = 5;
+      while ((1u << tl) < 2u * (unsigned)P2) tl++;
+      size_t per_warp = ((size_t)(1u << tl) + k * k) * sizeof(u32);
+      size_t fsmem = per_warp * 8;
+      dim3 block(256), grid(grid_for(rows * 32, 256));
+#define FAST_CASE(EE)                                                                              \
+  {                                                                                                \
+    if (fsmem > 48 * 1024)                                                                         \
+      cudaFuncSetAttribute(supercharge_fast_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem); \
+    supercharge_fast_kernel<EE><<<grid, block, fsmem, stream>>>(queries, points, own_ids, own_dist, graph, n, (int)k, row_begin, row_end, exclude_self, tl, out_ids, out_dist, flags); \
+  }
+      switch (epl) {
+        case 2: FAST_CASE(2) break;
+        case 4: FAST_CASE(4) break;
+        case 8: FAST_CASE(8) break;
+        default: FAST_CASE(16) break;
+      }
+#undef FAST_CASE
+      LAUNCH_CHECK("supercharge_fast");
+      all_literal_redo_only = true;
+    }
+  }
+#define SC_ARGS regs, smem, stream, queries, points, own_ids, own_dist, graph, n, (int)d, (int)k, row_begin, row_end, exclude_self, out_ids, out_dist, flags, slabs, slab_bytes, status, all_literal, all_literal_redo_only
   switch (mode) {
     case 0: launch_supercharge<0>(SC_ARGS); break;
     case 1: launch_supercharge<1>(SC_ARGS); break;

@@ -115,14 +115,14 @@ void annb_merge_lists(const annb_u32 *lists_ids, const ftype *lists_dist, int n_
 /* ---- S5: supercharging (supercharge + compdists + second sort_and_uniq, alg.c:313-335) --
  * For each query row x in [row_begin, row_end): candidates = own list ++ the lists of its
  * neighbours (graph rows), prefix 2^floor(log2(k(k+1))); distances from queries[x] to
- * points[id]; out rows are relative to row_begin.  exclude_self: the reference excludes
+ * points[id]; out rows are relative to row_begin (32-bit ids; the host widens them).  exclude_self: the reference excludes
  * id == x only when the query set IS the point set (compute.cl:145).
  * graph may be the merged ids themselves (precomp) or save->graph (query).
  * scratch: at least (row_end-row_begin) + 512 bytes plus room for literal rows.           */
 void annb_supercharge(const ftype *queries, const ftype *points, const annb_u32 *own_ids,
                       const ftype *own_dist, const annb_u32 *graph, size_t n, size_t d,
                       size_t k, size_t row_begin, size_t row_end, int exclude_self,
-                      size_t *out_ids, ftype *out_dist, void *scratch, size_t scratch_bytes,
+                      annb_u32 *out_ids, ftype *out_dist, void *scratch, size_t scratch_bytes,
                       int *status, annb_stream stream);
 
 /* number of kernels launched through this layer since the last reset (bench.py reports it) */
