@@ -12,6 +12,9 @@ typedef annb_u32 u32;
 #define FULL 0xffffffffu
 
 extern unsigned long annb_g_launches;
+// rows redone by the literal kernels: per-file device counters behind annb_literal_rows()
+unsigned long long annb_leaf_literal_count(int reset);
+void annb_finish_literal_counts(unsigned long long out[2], int reset);
 
 #define LAUNCH_CHECK(what)                                                              \
   do {                                                                                  \

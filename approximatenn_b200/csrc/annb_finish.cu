@@ -2,6 +2,13 @@
 // (exact-tie / short-row) counterparts.
 #include "annb_common.cuh"
 
+static __device__ unsigned long long finish_literal_rows_dev[2];
+void annb_finish_literal_counts(unsigned long long out[2], int reset) {
+  unsigned long long z[2] = {0, 0};
+  cudaMemcpyFromSymbol(out, finish_literal_rows_dev, sizeof z);
+  if (reset) cudaMemcpyToSymbol(finish_literal_rows_dev, z, sizeof z);
+}
+
 // =====================================================================================
 // S4: union of the per-try lists, one warp per point
 // =====================================================================================
@@ -93,6 +100,7 @@ merge_literal_kernel(const u32 *__restrict__ lists_ids, const FT *__restrict__ l
       int src = __ffs(flagged) - 1;
       flagged &= flagged - 1;
       const size_t x = base + src;
+      if (lane == 0) atomicAdd(&finish_literal_rows_dev[0], 1ull);
       for (int e = lane; e < len; e += 32) {
         int t = e / k, z = e - t * k;
         ids[e] = lists_ids[((size_t)t * n + x) * k + z];
@@ -435,6 +443,7 @@ supercharge_literal_kernel(const FT *__restrict__ queries, const FT *__restrict_
       int src = __ffs(flagged) - 1;
       flagged &= flagged - 1;
       const size_t orow = base + src, x = row_begin + orow;
+      if (lane == 0) atomicAdd(&finish_literal_rows_dev[1], 1ull);
       for (int e = lane; e < k; e += 32) {
         ids[e] = own_ids[x * (size_t)k + e];
         key[e] = own_dist[x * (size_t)k + e];

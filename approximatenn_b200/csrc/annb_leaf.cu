@@ -13,6 +13,14 @@
 //                           matter with the reference's literal row + sorting network.
 #include "annb_common.cuh"
 
+static __device__ unsigned long long leaf_literal_rows_dev;
+unsigned long long annb_leaf_literal_count(int reset) {
+  unsigned long long v = 0, z = 0;
+  cudaMemcpyFromSymbol(&v, leaf_literal_rows_dev, sizeof v);
+  if (reset) cudaMemcpyToSymbol(leaf_literal_rows_dev, &z, sizeof z);
+  return v;
+}
+
 // =====================================================================================
 // generic: one warp per point
 // =====================================================================================
@@ -195,7 +203,8 @@ __global__ void __launch_bounds__(TILE_WARPS * 32)
 leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
                       const u32 *__restrict__ offset, const u32 *__restrict__ tmax_p, size_t n,
                       size_t buckets, int d_short, int k, u32 *__restrict__ list_ids,
-                      FT *__restrict__ list_dist, unsigned char *__restrict__ tie_flags) {
+                      FT *__restrict__ list_dist, unsigned char *__restrict__ tie_flags,
+                      int pack_tries, int max_slices) {
   typedef TileSmem<D, KC> SM;
   constexpr int RS = SM::RS;
   constexpr int PPR = D / VW;                                          // 16-byte pieces per row
@@ -241,12 +250,28 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
   }
   __syncwarp();
   const u32 C = segpos[32];
-  const u32 nchunks = (C + TILE_CH - 1) / TILE_CH;
 
-  for (u32 qbase = 0; qbase < Q; qbase += 32) {
-    const u32 Qp = min(32u, Q - qbase);
-    const int S = Qp <= 4 ? 8 : Qp <= 8 ? 4 : Qp <= 16 ? 2 : 1;       // candidate slices
-    const int per = TILE_CH / S;
+  // Queries are packed as (query, slice): S slices of the candidate stream per query, so that
+  // Qp*S lanes work.  The bucket is cut into `passes` groups of qpp queries where that
+  // fills the warp better (cost ~ passes / S candidate scans).
+  int passes = (int)((Q + 31) / 32), S = 1;
+  {
+    float best = 1e30f;
+    const int t0 = passes;
+    for (int t = t0; t < t0 + pack_tries; t++) {
+      int qpp_t = (int)((Q + t - 1) / t);
+      int s_t = min(max_slices, 32 / qpp_t);
+      float cost = (float)t / (float)s_t;
+      if (cost < best - 1e-6f) { best = cost; passes = t; S = s_t; }
+    }
+  }
+  const u32 qpp = (Q + passes - 1) / passes;
+  const int per = TILE_CH / S;                                     // candidates per lane per chunk
+  const u32 CHS = (u32)(S * per);                                   // rows staged per chunk
+  const u32 nchunks = (C + CHS - 1) / CHS;
+
+  for (u32 qbase = 0; qbase < Q; qbase += qpp) {
+    const u32 Qp = min(qpp, Q - qbase);
     const bool active = lane < (int)(Qp * S);
     const int s = active ? lane / (int)Qp : 0;
     const int qi = active ? lane - s * (int)Qp : 0;
@@ -269,18 +294,20 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
     for (int i = 0; i < KC; i++) { ld[i] = ft_inf(); li[i] = sentinel; }
     bool tie = false;
     int cnt = 0;
+    int seg_y = 0;                                                  // this lane's segment cursor
 
     auto stage_chunk = [&](u32 c, int buf) {
       // lanes 0..15 locate the rows of this chunk; every lane then copies 16-byte pieces
-      u32 j = c * TILE_CH + (lane & (TILE_CH - 1));
+      const u32 slot = lane & (TILE_CH - 1);
+      u32 j = c * CHS + slot;
+      const bool live = slot < CHS && j < C;
       u32 grow = 0;
-      if (j < C) {
-        int y = 0;
-        while (j >= segpos[y + 1]) y++;
-        grow = segrow[y] + (j - segpos[y]);
+      if (live) {
+        while (j >= segpos[seg_y + 1]) seg_y++;                   // chunks advance monotonically
+        grow = segrow[seg_y] + (j - segpos[seg_y]);
       }
       if (lane < TILE_CH) {
-        if (j < C) cp_async4(&cids[buf * TILE_CH + lane], order + grow);
+        if (live) cp_async4(&cids[buf * TILE_CH + lane], order + grow);
         else cids[buf * TILE_CH + lane] = sentinel;
       }
       FT *dst = rows + (size_t)buf * TILE_CH * RS;
@@ -289,7 +316,7 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
         int p = lane + 32 * it;
         int r = p / PPR, col = p - r * PPR;
         u32 gr = __shfl_sync(FULL, grow, r & (TILE_CH - 1));
-        if (p < TILE_CH * PPR) cp_async16(dst + r * RS + col * VW, sp + (size_t)gr * D + col * VW);
+        if (p < (int)CHS * PPR) cp_async16(dst + r * RS + col * VW, sp + (size_t)gr * D + col * VW);
       }
       cp_async_commit();
     };
@@ -310,29 +337,23 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
         bidx[cnt * 32 + lane] = cid;
         cnt++;
       }
-      if (cnt == KC) {
+      if (cnt + per > KC || c + 1 == nchunks) {
         FT bd[KC];
         u32 bi[KC];
 #pragma unroll
-        for (int i = 0; i < KC; i++) { bd[i] = bdist[i * 32 + lane]; bi[i] = bidx[i * 32 + lane]; }
+        for (int i = 0; i < KC; i++) {
+          bool have = i < cnt;
+          bd[i] = have ? bdist[i * 32 + lane] : ft_inf();
+          bi[i] = have ? bidx[i * 32 + lane] : sentinel;
+        }
         fold_batch<KC>(ld, li, bd, bi, true, tie);
         cnt = 0;
       }
       __syncwarp();
     }
-    if (cnt > 0) {
-      FT bd[KC];
-      u32 bi[KC];
-#pragma unroll
-      for (int i = 0; i < KC; i++) {
-        bool have = i < cnt;
-        bd[i] = have ? bdist[i * 32 + lane] : ft_inf();
-        bi[i] = have ? bidx[i * 32 + lane] : sentinel;
-      }
-      fold_batch<KC>(ld, li, bd, bi, true, tie);
-    }
     // fold the slices of each query together (lists are sorted: no batch sort needed)
-    for (int hs = S >> 1; hs >= 1; hs >>= 1) {
+    for (int sc = S; sc > 1;) {
+      const int hs = (sc + 1) >> 1;                                 // slices s < sc-hs take slice s+hs
       FT bd[KC];
       u32 bi[KC];
       int src = lane + hs * (int)Qp;
@@ -343,10 +364,11 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
         bi[i] = __shfl_sync(FULL, li[i], src);
       }
       bool other_tie = __shfl_sync(FULL, (int)tie, src);
-      if (s < hs) {
+      if (s + hs < sc) {
         fold_batch<KC>(ld, li, bd, bi, false, tie);
         tie |= other_tie;
       }
+      sc = hs;
     }
     if (active && s == 0) {
 #pragma unroll
@@ -402,17 +424,39 @@ leaf_literal_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
       int src = __ffs(flagged) - 1;
       flagged &= flagged - 1;
       const u32 x = (u32)(base + src);
+      if (lane == 0) atomicAdd(&leaf_literal_rows_dev, 1ull);
       const u32 h = hash[x];
       const size_t xr = rank_of[x];                               // sorted position of x
       for (int y = 0; y <= d_short; y++) {
         u32 b = h ^ (y ? (1u << (y - 1)) : 0u);
         u32 beg = offset[b], cnt = offset[b + 1] - beg;
         for (u32 z = lane; z < (u32)tmax; z += 32) ids[(size_t)y * tmax + z] = z < cnt ? order[beg + z] : sentinel;
-        for (u32 z = 0; z < (u32)tmax; z++) {
-          FT dist = ft_inf();
-          if (z < cnt && (size_t)beg + z != xr)
-            dist = row_sqdist<E>(sp + xr * (size_t)d, sp + ((size_t)beg + z) * d, d, tmp, lane);
-          if (lane == 0) key[(size_t)y * tmax + z] = dist;
+        if (E) {
+          WarpRow<(E ? E : 1)> qr;
+          qr.load(sp + xr * (size_t)d, lane, d);
+          for (u32 z0 = 0; z0 < cnt; z0 += 8) {                     // 8 candidate rows in flight
+            WarpRow<(E ? E : 1)> cr[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              size_t row = (size_t)beg + min(z0 + u, cnt - 1);
+              cr[u].load(sp + row * (size_t)d, lane, d);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              FT dist = __shfl_sync(FULL, warp_sqdist<(E ? E : 1)>(qr, cr[u], d), 0);
+              u32 z = z0 + u;
+              if ((size_t)beg + z == xr) dist = ft_inf();
+              if (lane == 0 && z < cnt) key[(size_t)y * tmax + z] = dist;
+            }
+          }
+          for (u32 z = cnt + lane; z < (u32)tmax; z += 32) key[(size_t)y * tmax + z] = ft_inf();
+        } else {
+          for (u32 z = 0; z < (u32)tmax; z++) {
+            FT dist = ft_inf();
+            if (z < cnt && (size_t)beg + z != xr)
+              dist = generic_sqdist(sp + xr * (size_t)d, sp + ((size_t)beg + z) * d, d, tmp, lane);
+            if (lane == 0) key[(size_t)y * tmax + z] = dist;
+          }
         }
       }
       __syncwarp();
@@ -467,7 +511,16 @@ static void launch_tile(annb_stream stream, const FT *sp, const u32 *order, cons
     configured = true;
   }
   unsigned grid = (unsigned)((buckets + TILE_WARPS - 1) / TILE_WARPS);
-  leaf_topk_tile_kernel<D, KC><<<grid, TILE_WARPS * 32, smem, stream>>>(sp, order, offset, tmax, n, buckets, d_short, k, ids, dist, flags);
+  static int pack_tries = -1, max_slices = 16;
+  if (pack_tries < 0) {
+    const char *e1 = getenv("ANN_B200_TILE_PASSES"), *e2 = getenv("ANN_B200_TILE_SLICES");
+    pack_tries = e1 && *e1 ? atoi(e1) : 3;
+    max_slices = e2 && *e2 ? atoi(e2) : 4;
+    if (pack_tries < 1) pack_tries = 1;
+    if (max_slices < 1) max_slices = 1;
+    if (max_slices > 16) max_slices = 16;
+  }
+  leaf_topk_tile_kernel<D, KC><<<grid, TILE_WARPS * 32, smem, stream>>>(sp, order, offset, tmax, n, buckets, d_short, k, ids, dist, flags, pack_tries, max_slices);
 }
 
 // returns false when no tiled instantiation covers (d, k)

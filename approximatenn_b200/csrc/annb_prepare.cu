@@ -10,6 +10,11 @@ extern "C" unsigned long annb_launch_count(int reset) {
   return v;
 }
 
+extern "C" void annb_literal_rows(unsigned long long out[3], int reset) {
+  out[0] = annb_leaf_literal_count(reset);
+  annb_finish_literal_counts(out + 1, reset);
+}
+
 // =====================================================================================
 // S0: column means
 // =====================================================================================
@@ -138,6 +143,103 @@ hash_points_kernel(const FT *__restrict__ points, const FT *__restrict__ mean,
   }
 }
 
+// Register variant for d_max in {16,32,64,128}: the Walsh-Hadamard butterflies run on a
+// fully unrolled register array (compile-time indices), shared memory only carries the
+// data-dependent accesses: the "before" sweeps, the sub-permutation gather, the "after"
+// sweeps and the projection picks.  V0 keeps the centred tile for all tries (one global
+// read of the points); W is the per-try working plane (rotated row, then transformed row).
+template <int DM, int TP>
+__global__ void __launch_bounds__(TP)
+hash_points_reg_kernel(const FT *__restrict__ points, const FT *__restrict__ mean,
+                       annb_transform_desc t, u32 *__restrict__ hash) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int LD = TP + 1;
+  constexpr int LEVELS = DM == 16 ? 4 : DM == 32 ? 5 : DM == 64 ? 6 : 7;
+  const int d = (int)t.d;
+  FT *V0 = reinterpret_cast<FT *>(smem_raw);
+  FT *W = V0 + (size_t)d * LD;
+  const int tid = threadIdx.x;
+  const size_t tiles = (t.n + TP - 1) / TP;
+  const int planes_b = (int)(t.rots_before * t.rot_len_before);
+  const int planes_all = planes_b + (int)(t.rots_after * t.rot_len_after);
+  const int ds = (int)t.d_short;
+
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const size_t p0 = tile * TP;
+    const size_t rows = (t.n - p0 < (size_t)TP) ? t.n - p0 : (size_t)TP;
+    __syncthreads();
+    for (size_t e = tid; e < rows * d; e += TP) {
+      size_t r = e / d, c = e - r * d;
+      V0[c * LD + r] = points[p0 * d + e] - mean[c];            // compute.cl:44-49
+    }
+    __syncthreads();
+    if ((size_t)tid >= rows) continue;
+    for (int tr = 0; tr < t.tries; tr++) {
+      const u32 *pidx = t.plane_idx + (size_t)tr * planes_all * 2;
+      const FT *pcs = t.plane_cs + (size_t)tr * planes_all * 2;
+      const u32 *permb = t.perm_b + (size_t)tr * DM;
+      const u32 *pick = t.pick + (size_t)tr * ds;
+      for (int c = 0; c < d; c++) W[c * LD + tid] = V0[c * LD + tid];
+      for (int q = 0; q < planes_b; q++) {                       // compute.cl:55-68
+        u32 i = pidx[2 * q], j = pidx[2 * q + 1];
+        FT c = pcs[2 * q], sn = pcs[2 * q + 1];
+        FT a = W[i * LD + tid], b = W[j * LD + tid];
+        W[i * LD + tid] = a * c - b * sn;
+        W[j * LD + tid] = a * sn + b * c;
+      }
+      FT z[DM];
+#pragma unroll
+      for (int y = 0; y < DM; y++) {                             // compute.cl:77-85
+        u32 src = permb[y];
+        z[y] = src < (u32)d ? W[src * LD + tid] : (FT)0;
+      }
+#pragma unroll
+      for (int lev = 0; lev < LEVELS; lev++) {                   // compute.cl:101-122
+#pragma unroll
+        for (int w = 0; w < DM / 2; w++) {
+          const int hi_part = (w >> lev) << lev, lo_part = w ^ hi_part;
+          const int ia = (hi_part << 1) | lo_part, ib = ia | (1 << lev);
+          FT a = z[ia], b = z[ib];
+          FT sm = a + b, df = a - b;
+          if (lev & 1) { sm *= (FT)0.5; df *= (FT)0.5; }
+          if (lev == 0 && (LEVELS & 1)) { sm *= t.inv_sqrt2; df *= t.inv_sqrt2; }
+          z[ia] = sm;
+          z[ib] = df;
+        }
+      }
+#pragma unroll
+      for (int y = 0; y < DM; y++) W[y * LD + tid] = z[y];
+      for (int q = planes_b; q < planes_all; q++) {
+        u32 i = pidx[2 * q], j = pidx[2 * q + 1];
+        FT c = pcs[2 * q], sn = pcs[2 * q + 1];
+        FT a = W[i * LD + tid], b = W[j * LD + tid];
+        W[i * LD + tid] = a * c - b * sn;
+        W[j * LD + tid] = a * sn + b * c;
+      }
+      u32 h = 0;
+      for (int i = 0; i < ds; i++) h = (h << 1) | sign_bit(W[pick[i] * LD + tid]);
+      hash[(size_t)tr * t.n + p0 + tid] = h;
+    }
+  }
+}
+
+template <int DM>
+static bool launch_hash_reg(const FT *points, const FT *mean, const annb_transform_desc *t, u32 *hash,
+                            annb_stream stream) {
+  constexpr int TP = 128;
+  size_t smem = (t->d + DM) * (size_t)(TP + 1) * sizeof(FT);
+  if (smem > 200 * 1024) return false;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(hash_points_reg_kernel<DM, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+  size_t tiles = (t->n + TP - 1) / TP;
+  unsigned grid = (unsigned)(tiles < 148 * 8 ? tiles : 148 * 8);
+  hash_points_reg_kernel<DM, TP><<<grid, TP, smem, stream>>>(points, mean, *t, hash);
+  return true;
+}
+
 static const int HASH_TP = 128;
 static const size_t HASH_SMEM_LIMIT = 200 * 1024;
 static const unsigned HASH_SCRATCH_GRID = 148 * 4;
@@ -153,6 +255,22 @@ extern "C" size_t annb_hash_scratch_bytes(const annb_transform_desc *t) {
 
 extern "C" void annb_hash_points(const FT *points, const FT *mean, const annb_transform_desc *t,
                                  u32 *hash, void *scratch, annb_stream stream) {
+  {
+    const char *off = getenv("ANN_B200_NO_REG_HASH");
+    bool done = false;
+    if (!(off && *off && *off != '0')) {
+      switch (t->d_max) {
+        case 16: done = launch_hash_reg<16>(points, mean, t, hash, stream); break;
+        case 32: done = launch_hash_reg<32>(points, mean, t, hash, stream); break;
+        case 64: done = launch_hash_reg<64>(points, mean, t, hash, stream); break;
+#ifdef USE_FLOAT
+        case 128: done = launch_hash_reg<128>(points, mean, t, hash, stream); break;
+#endif
+        default: break;
+      }
+    }
+    if (done) { LAUNCH_CHECK("hash_points_reg"); return; }
+  }
   size_t tiles = (t->n + HASH_TP - 1) / HASH_TP;
   size_t need = hash_plane_bytes(t);
   if (need <= HASH_SMEM_LIMIT) {

@@ -125,6 +125,9 @@ void annb_supercharge(const ftype *queries, const ftype *points, const annb_u32 
                       annb_u32 *out_ids, ftype *out_dist, void *scratch, size_t scratch_bytes,
                       int *status, annb_stream stream);
 
+/* rows redone by the literal kernels since the last reset: [0] S3, [1] S4, [2] S5 (synchronous)  */
+void annb_literal_rows(unsigned long long out[3], int reset);
+
 /* number of kernels launched through this layer since the last reset (bench.py reports it) */
 unsigned long annb_launch_count(int reset);
 
