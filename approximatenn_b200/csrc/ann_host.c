@@ -104,13 +104,14 @@ void gpu_cleanup(void) {
 }
 
 void *annh_stream(void) { gpu_init(); return G.stream; }
+int annh_device(void) { gpu_init(); return G.device; }
 const annh_stage_times *annh_last_times(void) { return &G.last; }
 void annh_set_timing(int on) { gpu_init(); G.timing = on; }
 
 /* ------------------------------------------------------------------------------------ */
 /* device arena                                                                          */
 
-static void arena_reserve(size_t bytes) {
+void annh_arena_reserve(size_t bytes) {
   if (bytes <= G.arena_bytes) { G.arena_used = 0; return; }
   if (G.arena) {
     CK(cudaStreamSynchronize(G.stream));
@@ -130,7 +131,7 @@ static void arena_reserve(size_t bytes) {
 
 static size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-static void *arena_take(size_t bytes) {
+void *annh_arena_take(size_t bytes) {
   size_t at = G.arena_used;
   G.arena_used += pad256(bytes);
   if (G.arena_used > G.arena_bytes) annh_fatal("internal: %s", "device arena overrun");
@@ -347,27 +348,27 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   size_t group = T;                                            /* lists kept before a merge */
   while (group > 1 && fixed + group * list_bytes + 512 > free_b * 9 / 10) group--;
   if ((size_t)k * T < 16) group = T;
-  arena_reserve(fixed + group * list_bytes + 512);
+  annh_arena_reserve(fixed + group * list_bytes + 512);
 
-  ftype *dX = arena_take(n * d * w), *dXs = arena_take(n * d * w), *dmean = arena_take(d * w);
-  annb_u32 *dhash = arena_take(T * n * 4);
-  annb_u32 *dcount = arena_take(buckets * 4), *doffset = arena_take((buckets + 1) * 4);
-  annb_u32 *dorder_tmp = arena_take(n * 4), *dorder = arena_take(n * 4);
-  annb_u32 *dtmax = arena_take(T * 4);
-  void *dscan = arena_take(annb_scan_tmp_bytes(buckets));
-  annb_u32 *d_idx = arena_take(T * planes * 2 * 4 + 4);
-  ftype *d_cs = arena_take(T * planes * 2 * w + w);
-  annb_u32 *d_permb = arena_take(T * d_max * 4), *d_pick = arena_take(T * d_short * 4 + 4);
-  void *dhscratch = arena_take(annb_hash_scratch_bytes(&desc));
-  annb_u32 *dl_ids = arena_take(group * n * k * 4);
-  ftype *dl_dist = arena_take(group * n * k * w);
-  annb_u32 *dm_ids = arena_take(n * k * 4), *dm_ids2 = arena_take(n * k * 4);
-  ftype *dm_dist = arena_take(n * k * w), *dm_dist2 = arena_take(n * k * w);
-  annb_u32 *dout_ids = arena_take(n * k * 4);
-  ftype *dout_dist = arena_take(n * k * w);
+  ftype *dX = annh_arena_take(n * d * w), *dXs = annh_arena_take(n * d * w), *dmean = annh_arena_take(d * w);
+  annb_u32 *dhash = annh_arena_take(T * n * 4);
+  annb_u32 *dcount = annh_arena_take(buckets * 4), *doffset = annh_arena_take((buckets + 1) * 4);
+  annb_u32 *dorder_tmp = annh_arena_take(n * 4), *dorder = annh_arena_take(n * 4);
+  annb_u32 *dtmax = annh_arena_take(T * 4);
+  void *dscan = annh_arena_take(annb_scan_tmp_bytes(buckets));
+  annb_u32 *d_idx = annh_arena_take(T * planes * 2 * 4 + 4);
+  ftype *d_cs = annh_arena_take(T * planes * 2 * w + w);
+  annb_u32 *d_permb = annh_arena_take(T * d_max * 4), *d_pick = annh_arena_take(T * d_short * 4 + 4);
+  void *dhscratch = annh_arena_take(annb_hash_scratch_bytes(&desc));
+  annb_u32 *dl_ids = annh_arena_take(group * n * k * 4);
+  ftype *dl_dist = annh_arena_take(group * n * k * w);
+  annb_u32 *dm_ids = annh_arena_take(n * k * 4), *dm_ids2 = annh_arena_take(n * k * 4);
+  ftype *dm_dist = annh_arena_take(n * k * w), *dm_dist2 = annh_arena_take(n * k * w);
+  annb_u32 *dout_ids = annh_arena_take(n * k * 4);
+  ftype *dout_dist = annh_arena_take(n * k * w);
   const size_t scratch_bytes = annb_leaf_scratch_bytes(n);
-  void *dscratch = arena_take(scratch_bytes);
-  int *dstatus = arena_take(sizeof(int));
+  void *dscratch = annh_arena_take(scratch_bytes);
+  int *dstatus = annh_arena_take(sizeof(int));
   CK(cudaMemsetAsync(dstatus, 0, sizeof(int), st));
 
   /* 3. upload                                                                          */

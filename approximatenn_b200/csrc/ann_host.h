@@ -15,8 +15,13 @@ void annh_fatal(const char *fmt, const char *detail);
 /* d_short / d_max of a problem (alg.c:347-357) */
 void annh_params(size_t n, size_t k, size_t d, size_t *d_short, size_t *d_max);
 
-/* the library's CUDA stream (cudaStream_t), after gpu_init() */
+/* the library's CUDA stream (cudaStream_t) and device, after gpu_init() */
 void *annh_stream(void);
+int annh_device(void);
+
+/* per-call device arena (one allocation reused across calls, grown on demand)           */
+void annh_arena_reserve(size_t bytes);
+void *annh_arena_take(size_t bytes);
 
 /* Device-time of the stages of the last precomp_gpu call, measured with CUDA events on
  * the library stream when timing is on (annh_set_timing(1) or ANN_B200_TIMING=1).

@@ -1,14 +1,184 @@
-/* ann_query.c — query_gpu.  Placeholder until the device path
- * lands: it fails loudly instead of answering from the CPU. */
+/* ann_query.c — query_gpu (alg.c:458-519 on the device).
+ *
+ * The reference re-wraps points, graph, bucket tables and bases as device buffers on every
+ * call (alg.c:464-508).  Here the index is uploaded once and kept on the device, keyed on
+ * the save_t it came from; free_save() drops it.  Because save_t has
+ * no spare field, the key is (graph pointer, points pointer, shape) plus a fingerprint of
+ * sampled graph/table/point entries, so a recycled allocation is not mistaken for the old
+ * index.  ANN_B200_QUERY_CACHE=0 rebuilds the device copy on every call.
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <cuda_runtime_api.h>
+
 #include "ann.h"
 #include "algg.h"
+#include "gpu_comp.h"
+#include "annb200.h"
 #include "ann_host.h"
 
-void annh_forget_save(const save_t *save) { (void)save; }
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      fprintf(stderr, "approximatenn_b200: %s failed at %s:%d: %s\n", #call, __FILE__,  \
+              __LINE__, cudaGetErrorString(e_));                                        \
+      exit(1);                                                                          \
+    }                                                                                   \
+  } while (0)
+
+typedef struct {
+  int live;
+  const size_t *graph_key;
+  const ftype *points_key;
+  size_t n, k, d_short, d, tries;
+  uint64_t fingerprint;
+  ftype *d_points, *d_mean, *d_bases;
+  annb_u32 *d_graph;
+  annb_u32 **d_tab;            /* host array of device pointers */
+  annb_u32 **d_tab_dev;        /* the same array on the device  */
+} device_index;
+
+static device_index IDX;
+static int cleanup_registered;
+
+static uint64_t mix(uint64_t h, uint64_t v) {
+  h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+  return h;
+}
+
+static uint64_t fingerprint(const save_t *s, const ftype *points) {
+  uint64_t h = 1469598103934665603ull;
+  size_t cells = s->n * s->k, step = cells / 61 + 1;
+  for (size_t i = 0; i < cells; i += step) h = mix(h, s->graph[i]);
+  for (int t = 0; t < s->tries; t++) {
+    h = mix(h, s->par_maxes[t]);
+    size_t tc = s->par_maxes[t] << s->d_short, ts = tc / 17 + 1;
+    for (size_t i = 0; i < tc; i += ts) h = mix(h, s->which_par[t][i]);
+  }
+  size_t pc = s->n * s->d_long, ps = pc / 61 + 1;
+  for (size_t i = 0; i < pc; i += ps) {
+    uint64_t b = 0;
+    memcpy(&b, points + i, sizeof(ftype));
+    h = mix(h, b);
+  }
+  return h;
+}
+
+static void drop_index(void) {
+  if (!IDX.live) return;
+  CK(cudaStreamSynchronize((cudaStream_t)annh_stream()));
+  CK(cudaFree(IDX.d_points)); CK(cudaFree(IDX.d_mean)); CK(cudaFree(IDX.d_bases));
+  CK(cudaFree(IDX.d_graph));
+  for (size_t t = 0; t < IDX.tries; t++) CK(cudaFree(IDX.d_tab[t]));
+  CK(cudaFree(IDX.d_tab_dev));
+  free(IDX.d_tab);
+  memset(&IDX, 0, sizeof IDX);
+}
+
+void annh_forget_save(const save_t *save) {
+  if (IDX.live && IDX.graph_key == save->graph) drop_index();
+}
+
+static void upload_narrow(const size_t *host, size_t count, annb_u32 *dst, size_t *tmp, cudaStream_t st) {
+  CK(cudaMemcpyAsync(tmp, host, count * sizeof(size_t), cudaMemcpyHostToDevice, st));
+  annb_narrow_ids(tmp, count, dst, st);
+}
+
+static void build_index(const save_t *s, const ftype *points, uint64_t fp) {
+  drop_index();
+  cudaStream_t st = (cudaStream_t)annh_stream();
+  const size_t w = sizeof(ftype), T = (size_t)s->tries, B = (size_t)1 << s->d_short;
+  IDX.graph_key = s->graph; IDX.points_key = points;
+  IDX.n = s->n; IDX.k = s->k; IDX.d_short = s->d_short; IDX.d = s->d_long; IDX.tries = T;
+  IDX.fingerprint = fp;
+  CK(cudaMalloc((void **)&IDX.d_points, s->n * s->d_long * w));
+  CK(cudaMalloc((void **)&IDX.d_mean, s->d_long * w));
+  CK(cudaMalloc((void **)&IDX.d_bases, (T * s->d_short * s->d_long + 1) * w));
+  CK(cudaMalloc((void **)&IDX.d_graph, s->n * s->k * 4));
+  IDX.d_tab = calloc(T, sizeof(annb_u32 *));
+  size_t tmp_cells = s->n * s->k;
+  for (size_t t = 0; t < T; t++) {
+    size_t cells = B * s->par_maxes[t];
+    CK(cudaMalloc((void **)&IDX.d_tab[t], (cells ? cells : 1) * 4));
+    if (cells > tmp_cells) tmp_cells = cells;
+  }
+  size_t *tmp = NULL;
+  CK(cudaMalloc((void **)&tmp, tmp_cells * sizeof(size_t)));
+  CK(cudaMemcpyAsync(IDX.d_points, points, s->n * s->d_long * w, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(IDX.d_mean, s->row_means, s->d_long * w, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(IDX.d_bases, s->bases, T * s->d_short * s->d_long * w, cudaMemcpyHostToDevice, st));
+  upload_narrow(s->graph, s->n * s->k, IDX.d_graph, tmp, st);
+  for (size_t t = 0; t < T; t++) upload_narrow(s->which_par[t], B * s->par_maxes[t], IDX.d_tab[t], tmp, st);
+  CK(cudaMalloc((void **)&IDX.d_tab_dev, T * sizeof(annb_u32 *)));
+  CK(cudaMemcpyAsync(IDX.d_tab_dev, IDX.d_tab, T * sizeof(annb_u32 *), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaFree(tmp));
+  IDX.live = 1;
+  if (!cleanup_registered) {
+    register_cleanup(drop_index);
+    cleanup_registered = 1;
+  }
+}
 
 size_t *query_gpu(const save_t *save, const ftype *points, size_t ycnt, const ftype *y,
                   ftype **dists_o) {
-  (void)save; (void)points; (void)ycnt; (void)y; (void)dists_o;
-  annh_fatal("%s", "query_gpu is not built yet");
-  return NULL;
+  gpu_init();
+  cudaStream_t st = (cudaStream_t)annh_stream();
+  const size_t n = save->n, k = save->k, d = save->d_long, ds = save->d_short, w = sizeof(ftype);
+  const size_t T = (size_t)save->tries;
+  if (n >= 0xFFFFFFFFull) annh_fatal("%s", "n must be below 2^32 - 1");
+  if (k > 256) annh_fatal("%s", "k > 256 is not supported");
+  if (ycnt == 0) {
+    if (dists_o) *dists_o = malloc(1);
+    return malloc(1);
+  }
+  const char *env = getenv("ANN_B200_QUERY_CACHE");
+  int use_cache = !(env && *env == '0');
+  uint64_t fp = fingerprint(save, points);
+  if (!(use_cache && IDX.live && IDX.graph_key == save->graph && IDX.points_key == points &&
+        IDX.n == n && IDX.k == k && IDX.d_short == ds && IDX.d == d && IDX.tries == T &&
+        IDX.fingerprint == fp))
+    build_index(save, points, fp);
+
+  annh_egress *eg = annh_egress_begin(ycnt, k, dists_o != NULL, annh_device());
+  const size_t scratch_bytes = ycnt + 512 + ((size_t)64 << 20);
+  size_t need = (ycnt * d * w + 256) + (T * ycnt * 4 + 256) + 2 * (ycnt * k * 4 + 256) +
+                2 * (ycnt * k * w + 256) + scratch_bytes + 4096;
+  annh_arena_reserve(need);
+  ftype *dy = annh_arena_take(ycnt * d * w);
+  annb_u32 *dsign = annh_arena_take(T * ycnt * 4);
+  annb_u32 *down_ids = annh_arena_take(ycnt * k * 4), *dout_ids = annh_arena_take(ycnt * k * 4);
+  ftype *down_dist = annh_arena_take(ycnt * k * w), *dout_dist = annh_arena_take(ycnt * k * w);
+  void *dscratch = annh_arena_take(scratch_bytes);
+  int *dstatus = annh_arena_take(sizeof(int));
+  CK(cudaMemsetAsync(dstatus, 0, sizeof(int), st));
+
+  const int same_set = (y == points);                        /* compute.cl:145 pointer test */
+  const ftype *dq = dy;
+  if (same_set && ycnt <= n) dq = IDX.d_points;
+  else CK(cudaMemcpyAsync(dy, y, ycnt * d * w, cudaMemcpyHostToDevice, st));
+
+  annb_query_hash(dq, IDX.d_mean, IDX.d_bases, ycnt, d, ds, (int)T, dsign, st);
+  annb_query_rows(dq, IDX.d_points, (const annb_u32 *const *)IDX.d_tab, save->par_maxes, (int)T,
+                  dsign, n, ycnt, d, ds, k, same_set, down_ids, down_dist, dscratch, scratch_bytes,
+                  dstatus, st);
+  int nch = annh_egress_chunks(eg);
+  for (int c = 0; c < nch; c++) {
+    size_t r0 = (ycnt * (size_t)c / nch) & ~(size_t)31;
+    size_t r1 = c + 1 == nch ? ycnt : (ycnt * (size_t)(c + 1) / nch) & ~(size_t)31;
+    annb_supercharge(dq, IDX.d_points, down_ids, down_dist, IDX.d_graph, n, d, k, r0, r1, same_set,
+                     dout_ids + r0 * k, dists_o ? dout_dist + r0 * k : NULL, dscratch, scratch_bytes,
+                     dstatus, st);
+    annh_egress_chunk(eg, r0, r1, dout_ids + r0 * k, dout_dist + r0 * k, st);
+  }
+  int h_status = 0;
+  CK(cudaMemcpyAsync(&h_status, dstatus, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  size_t *result = annh_egress_end(eg, dists_o);
+  if (h_status) annh_fatal("%s", "scratch too small for a literal candidate row");
+  if (!use_cache) drop_index();
+  return result;
 }

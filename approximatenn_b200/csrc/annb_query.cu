@@ -1,0 +1,281 @@
+// annb_query.cu — the query path (alg.c:438-519): projection + sign hash of the query
+// vectors, candidate rows out of the saved bucket tables, k best per query.  The final
+// supercharging step is annb_supercharge() (annb_finish.cu) with graph = save->graph.
+#include "annb_common.cuh"
+
+static __device__ unsigned long long query_literal_rows_dev;
+unsigned long long annb_query_literal_count(int reset) {
+  unsigned long long v = 0, z = 0;
+  cudaMemcpyFromSymbol(&v, query_literal_rows_dev, sizeof v);
+  if (reset) cudaMemcpyToSymbol(query_literal_rows_dev, &z, sizeof z);
+  return v;
+}
+
+// =====================================================================================
+// Q1: hash of (query x, try t) = sign bits of (y_x - mean) . bases[t][i], i < d_short
+// =====================================================================================
+// prods + add_up_cols + compute_signs (compute.cl:268-275,160-167,223-231).  The products
+// can be -0.0, so the "+ 0" of the reference's even tree levels is kept (it turns -0.0
+// into +0.0 and thereby fixes the sign bit of an all-zero sum).  One warp per (x, t); the
+// result is stored where the reference stores it: sign[x * tries + t].
+
+__device__ __forceinline__ FT warp_dot_tree(const FT *__restrict__ yrow, const FT *__restrict__ mean,
+                                            const FT *__restrict__ b, int d, FT *tmp, int lane) {
+  for (int z = lane; z < d; z += 32) tmp[z] = (yrow[z] - mean[z]) * b[z];
+  __syncwarp();
+  for (int l = d; l >> 1; l >>= 1) {
+    int h = l >> 1;
+    for (int z = lane; z < h; z += 32) {
+      FT extra = (z == 0 && (l & 1)) ? tmp[l - 1] : (FT)0;
+      tmp[z] = tmp[z] + (tmp[z + h] + extra);
+    }
+    __syncwarp();
+  }
+  FT v = tmp[0];
+  __syncwarp();
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+query_hash_kernel(const FT *__restrict__ y, const FT *__restrict__ mean, const FT *__restrict__ bases,
+                  size_t ycnt, int d, int d_short, int tries, u32 *__restrict__ sign) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= ycnt * (size_t)tries) return;
+  FT *tmp = reinterpret_cast<FT *>(smem_raw) + (size_t)wib * d;
+  size_t x = w / tries;
+  int t = (int)(w - x * tries);
+  u32 h = 0;
+  for (int i = 0; i < d_short; i++) {
+    FT v = warp_dot_tree(y + x * (size_t)d, mean, bases + ((size_t)t * d_short + i) * d, d, tmp, lane);
+    h = (h << 1) | sign_bit(v);
+  }
+  if (lane == 0) sign[w] = h;
+}
+
+extern "C" void annb_query_hash(const FT *y, const FT *mean, const FT *bases, size_t ycnt, size_t d,
+                                size_t d_short, int tries, u32 *sign, annb_stream stream) {
+  size_t smem = 8 * d * sizeof(FT);
+  if (smem > 200 * 1024) fatal_config("d too large for the query projection");
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(query_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  query_hash_kernel<<<grid_for(ycnt * tries * 32, 256), 256, smem, stream>>>(y, mean, bases, ycnt, (int)d, (int)d_short, tries, sign);
+  LAUNCH_CHECK("query_hash");
+}
+
+// =====================================================================================
+// Q2: candidate rows from the saved tables -> k best per query
+// =====================================================================================
+// Row of query x (alg.c:438-452,493-511): for try i, columns
+// [(d_short+1)*off_i + f*w_i, +w_i) hold table_i[h_i ^ flip_f], off_i = sum of par_maxes
+// before i, w_i = par_maxes[i]; h_i = sign[i*ycnt + x] — the reference reads the sign
+// buffer with that layout although it was written as [x][try] (SURVEY "three facts" #3);
+// reproduced as is.  The first 2^floor(log2(len)) columns compete.
+struct QueryTables {
+  const u32 *tab[64];      // [2^d_short][w_i] padded with n, ids descending
+  u32 width[64];
+  u32 offset[64];
+  int tries;
+  unsigned long long len, prefix;
+};
+
+template <int E, int R>
+__global__ void __launch_bounds__(256)
+query_rows_kernel(const FT *__restrict__ y, const FT *__restrict__ points, QueryTables q,
+                  const u32 *__restrict__ sign, size_t n, size_t ycnt, int d, int d_short, int k,
+                  int exclude_self, u32 *__restrict__ list_ids, FT *__restrict__ list_dist,
+                  unsigned char *__restrict__ tie_flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  size_t x = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (x >= ycnt) return;
+  FT *tmp = reinterpret_cast<FT *>(smem_raw) + (size_t)wib * (E == 0 ? d : 0);
+  const u32 sentinel = (u32)n;
+  WarpRow<(E ? E : 1)> qr;
+  const FT *qrow = y + x * (size_t)d;
+  if (E) qr.load(qrow, lane, d);
+  WarpList<R> best;
+  best.clear(sentinel);
+  FT tau = ft_inf(), max_v = -ft_inf();
+  u32 max_id = sentinel, corner_id = sentinel;
+  bool any_inf = false, tie = false, done = false;
+
+  for (int t = 0; t < q.tries && !done; t++) {
+    const u32 h = sign[(size_t)t * ycnt + x];
+    const u32 w = q.width[t];
+    for (int f = 0; f <= d_short; f++) {
+      unsigned long long col = (unsigned long long)(d_short + 1) * q.offset[t] + (unsigned long long)f * w;
+      const u32 *row = q.tab[t] + (size_t)(h ^ (f ? (1u << (f - 1)) : 0u)) * w;
+      if (col >= q.prefix) {
+        // first slot outside the prefix is in this segment iff col == prefix
+        if (col == q.prefix && w) corner_id = row[0];
+        done = true;
+        break;
+      }
+      unsigned long long room = q.prefix - col;
+      u32 take = w < room ? w : (u32)room;
+      if (take < w) { corner_id = row[take]; done = true; }
+      for (u32 z = 0; z < take; z++) {
+        u32 id = row[z];
+        if (id >= sentinel) { any_inf = true; break; }          // pads fill the rest of the row
+        if (exclude_self && id == (u32)x) { any_inf = true; continue; }
+        FT dist;
+        if (E) {
+          WarpRow<(E ? E : 1)> cr;
+          cr.load(points + (size_t)id * d, lane, d);
+          dist = __shfl_sync(FULL, warp_sqdist<(E ? E : 1)>(qr, cr, d), 0);
+        } else {
+          dist = generic_sqdist(qrow, points + (size_t)id * d, d, tmp, lane);
+        }
+        if (dist > max_v) { max_v = dist; max_id = id; }
+        consider<R>(best, tau, dist, id, k, sentinel, lane, tie);
+      }
+      if (done) break;
+    }
+  }
+  if (q.prefix < q.len && !any_inf && corner_id == max_id) best.remove(corner_id, sentinel, lane);
+#pragma unroll
+  for (int rr = 0; rr < R; rr++) {
+    int p = rr * 32 + lane;
+    if (p < k) {
+      list_ids[x * (size_t)k + p] = best.id[rr];
+      list_dist[x * (size_t)k + p] = best.v[rr];
+    }
+  }
+  if (tie && lane == 0) tie_flags[x] = 1;
+}
+
+// literal row of a flagged query: every column, the reference's network, first k out
+template <int E>
+__global__ void __launch_bounds__(256)
+query_literal_kernel(const FT *__restrict__ y, const FT *__restrict__ points, QueryTables q,
+                     const u32 *__restrict__ sign, size_t n, size_t ycnt, int d, int d_short, int k,
+                     int exclude_self, u32 *__restrict__ list_ids, FT *__restrict__ list_dist,
+                     const unsigned char *__restrict__ tie_flags, unsigned char *scratch,
+                     size_t scratch_bytes, int *status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  FT *tmp = reinterpret_cast<FT *>(smem_raw) + (size_t)wib * (E == 0 ? d : 0);
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const size_t L = (size_t)q.len;
+  const size_t slab = (L * (sizeof(u32) + sizeof(FT)) + 15) & ~(size_t)15;
+  const size_t slabs = slab ? scratch_bytes / slab : 0;
+  if (slabs == 0) { if (warp == 0 && lane == 0) *status = 1; return; }
+  const size_t workers = slabs < nwarps ? slabs : nwarps;
+  if (warp >= workers) return;
+  FT *key = reinterpret_cast<FT *>(scratch + warp * slab);
+  u32 *ids = reinterpret_cast<u32 *>(key + L);
+  const u32 sentinel = (u32)n;
+
+  for (size_t base = warp * 32; base < ycnt; base += workers * 32) {
+    size_t p = base + lane;
+    unsigned flagged = __ballot_sync(FULL, p < ycnt && (!tie_flags || tie_flags[p]));
+    while (flagged) {
+      int src = __ffs(flagged) - 1;
+      flagged &= flagged - 1;
+      const size_t x = base + src;
+      if (lane == 0) atomicAdd(&query_literal_rows_dev, 1ull);
+      for (int t = 0; t < q.tries; t++) {
+        const u32 h = sign[(size_t)t * ycnt + x];
+        const u32 w = q.width[t];
+        for (int f = 0; f <= d_short; f++) {
+          size_t col = (size_t)(d_short + 1) * q.offset[t] + (size_t)f * w;
+          const u32 *row = q.tab[t] + (size_t)(h ^ (f ? (1u << (f - 1)) : 0u)) * w;
+          for (u32 z = lane; z < w; z += 32) ids[col + z] = row[z];
+          for (u32 z = 0; z < w; z++) {
+            u32 id = row[z];
+            FT dist = ft_inf();
+            if (id < sentinel && !(exclude_self && id == (u32)x))
+              dist = row_sqdist<E>(y + x * (size_t)d, points + (size_t)id * d, d, tmp, lane);
+            if (lane == 0) key[col + z] = dist;
+          }
+        }
+      }
+      __syncwarp();
+      warp_sort_and_uniq(ids, key, (int)L, lane);
+      for (int i = lane; i < k; i += 32) {
+        list_ids[x * (size_t)k + i] = ids[i];
+        list_dist[x * (size_t)k + i] = key[i];
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int E>
+static void launch_query_rows(int regs, size_t smem, annb_stream stream, const FT *y, const FT *points,
+                              const QueryTables &q, const u32 *sign, size_t n, size_t ycnt, int d,
+                              int d_short, int k, int ex, u32 *ids, FT *dist, unsigned char *flags,
+                              unsigned char *slabs, size_t slab_bytes, int *status) {
+  dim3 block(256), grid(grid_for(ycnt * 32, 256));
+#define QR_CASE(R)                                                                                \
+  {                                                                                               \
+    if (smem > 48 * 1024)                                                                         \
+      cudaFuncSetAttribute(query_rows_kernel<E, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    query_rows_kernel<E, R><<<grid, block, smem, stream>>>(y, points, q, sign, n, ycnt, d, d_short, k, ex, ids, dist, flags); \
+  }
+  switch (regs) {
+    case 1: QR_CASE(1) break;
+    case 2: QR_CASE(2) break;
+    case 4: QR_CASE(4) break;
+    default: QR_CASE(8) break;
+  }
+#undef QR_CASE
+  LAUNCH_CHECK("query_rows");
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(query_literal_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  query_literal_kernel<E><<<148, 256, smem, stream>>>(y, points, q, sign, n, ycnt, d, d_short, k, ex, ids, dist, flags, slabs, slab_bytes, status);
+  LAUNCH_CHECK("query_literal");
+}
+
+extern "C" void annb_query_rows(const FT *y, const FT *points, const u32 *const *tables,
+                                const size_t *par_maxes, int tries, const u32 *sign, size_t n,
+                                size_t ycnt, size_t d, size_t d_short, size_t k, int exclude_self,
+                                u32 *list_ids, FT *list_dist, void *scratch, size_t scratch_bytes,
+                                int *status, annb_stream stream) {
+  int regs = list_regs(k);
+  if (!regs) fatal_config("k > 256");
+  if (tries > 64) fatal_config("more than 64 tries in a saved index");
+  QueryTables q;
+  q.tries = tries;
+  unsigned long long off = 0;
+  for (int t = 0; t < tries; t++) {
+    q.tab[t] = tables[t];
+    q.width[t] = (u32)par_maxes[t];
+    q.offset[t] = (u32)off;
+    off += par_maxes[t];
+  }
+  q.len = off * (d_short + 1);
+  if (q.len < 16) fatal_config("query candidate rows shorter than 16 slots");
+  q.prefix = 1ull << (63 - __builtin_clzll(q.len));
+  int mode = row_mode(d);
+  size_t smem = mode ? 0 : 8 * d * sizeof(FT);
+  if (smem > 200 * 1024) fatal_config("d too large for the generic distance path");
+  unsigned char *flags = (unsigned char *)scratch;
+  unsigned char *slabs = (unsigned char *)(((uintptr_t)(flags + ycnt) + 255) & ~(uintptr_t)255);
+  size_t slab_bytes = scratch_bytes > ycnt + 512 ? scratch_bytes - ycnt - 512 : 0;
+  cudaMemsetAsync(flags, 0, ycnt, stream);
+#define Q_ARGS regs, smem, stream, y, points, q, sign, n, ycnt, (int)d, (int)d_short, (int)k, exclude_self, list_ids, list_dist, flags, slabs, slab_bytes, status
+  switch (mode) {
+    case 0: launch_query_rows<0>(Q_ARGS); break;
+    case 1: launch_query_rows<1>(Q_ARGS); break;
+    case 2: launch_query_rows<2>(Q_ARGS); break;
+    case 4: launch_query_rows<4>(Q_ARGS); break;
+    default: launch_query_rows<8>(Q_ARGS); break;
+  }
+#undef Q_ARGS
+}
+
+// size_t -> u32 narrowing of host-format tables / graphs already copied to the device
+__global__ void narrow_ids_kernel(const size_t *__restrict__ src, size_t count, u32 *__restrict__ dst) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[i] = (u32)src[i];
+}
+
+extern "C" void annb_narrow_ids(const size_t *src, size_t count, u32 *dst, annb_stream stream) {
+  if (!count) return;
+  narrow_ids_kernel<<<grid_for(count, 256), 256, 0, stream>>>(src, count, dst);
+  LAUNCH_CHECK("narrow_ids");
+}

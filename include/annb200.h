@@ -125,6 +125,24 @@ void annb_supercharge(const ftype *queries, const ftype *points, const annb_u32 
                       annb_u32 *out_ids, ftype *out_dist, void *scratch, size_t scratch_bytes,
                       int *status, annb_stream stream);
 
+/* ---- query path (alg.c:438-519) ----------------------------------------------------------
+ * annb_query_hash: prods + add_up_cols + compute_signs (compute.cl:268-275,160-167,223-231):
+ *   sign[x*tries + t] = sign bits of (y_x - mean) . bases[t][i], i < d_short.
+ * annb_query_rows: shufcomp + compdists + first sort_and_uniq of det_results: candidate row
+ *   of query x = for each try i the tables rows of h_i ^ flip_f, h_i = sign[i*ycnt + x] (the
+ *   reference's own, transposed, read of the sign buffer), prefix 2^floor(log2(len));
+ *   tables[i] is a HOST array entry holding a DEVICE pointer to the 32-bit padded table
+ *   [2^d_short][par_maxes[i]]; par_maxes is a host array.  list_*: [ycnt][k].
+ * annb_narrow_ids: size_t -> 32-bit ids on the device (host-format tables / graph).        */
+void annb_query_hash(const ftype *y, const ftype *mean, const ftype *bases, size_t ycnt, size_t d,
+                     size_t d_short, int tries, annb_u32 *sign, annb_stream stream);
+void annb_query_rows(const ftype *y, const ftype *points, const annb_u32 *const *tables,
+                     const size_t *par_maxes, int tries, const annb_u32 *sign, size_t n,
+                     size_t ycnt, size_t d, size_t d_short, size_t k, int exclude_self,
+                     annb_u32 *list_ids, ftype *list_dist, void *scratch, size_t scratch_bytes,
+                     int *status, annb_stream stream);
+void annb_narrow_ids(const size_t *src, size_t count, annb_u32 *dst, annb_stream stream);
+
 /* rows redone by the literal kernels since the last reset: [0] S3, [1] S4, [2] S5 (synchronous)  */
 void annb_literal_rows(unsigned long long out[3], int reset);
 
