@@ -21,6 +21,7 @@
 #include "gpu_comp.h"
 #include "annb200.h"
 #include "ann_host.h"
+#include "annb200_dist.h"
 
 /* ------------------------------------------------------------------------------------ */
 /* errors, lifecycle                                                                     */
@@ -299,28 +300,46 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   validate(n, k, d, tries, rot_len_before, rot_len_after, d_short);
   const size_t T = (size_t)tries, buckets = (size_t)1 << d_short;
   const size_t planes = rots_before * rot_len_before + rots_after * rot_len_after;
+  const size_t w = sizeof(ftype);
   cudaStream_t st = G.stream;
-  annh_egress *eg = annh_egress_begin(n, k, dists_o != NULL, G.device);
 
-  /* 1. transforms: ALL tries are drawn before any compute (alg.c:388-392)              */
+  /* sharding (ann_dist.c): rank r owns tries t = r, r+R, ... and the rows [row_lo, row_hi)  */
+  const int R = annh_dist_world(), rank = annh_dist_rank();
+  const int sharded = R > 1;
+  size_t row_lo = 0, row_hi = n;
+  if (sharded) annb200_dist_slice(n, rank, R, &row_lo, &row_hi);
+  const size_t my_rows = row_hi - row_lo;
+  size_t Tl = 0;                                               /* tries owned by this rank  */
+  for (size_t t = 0; t < T; t++) Tl += annb200_dist_try_owner((int)t, R) == rank;
+  if (sharded && save) annh_fatal("%s", "save != NULL is not supported in sharded mode yet");
+  if (sharded && T > 64) annh_fatal("%s", "more than 64 tries in sharded mode");
+  const int full_result = !sharded || annh_dist_gather_results();
+  const size_t out_rows = full_result ? n : my_rows;
+  annh_egress *eg = annh_egress_begin(out_rows, k, dists_o != NULL, G.device);
+
+  /* 1. transforms: ALL tries are drawn before any compute (alg.c:388-392), on every rank   */
   host_transform *tf = malloc(sizeof(host_transform) * T);
   for (size_t t = 0; t < T; t++)
     draw_transform(tf + t, rots_before, rot_len_before, rots_after, rot_len_after, d_short, d, d_max);
-  annb_u32 *h_idx = malloc(sizeof(annb_u32) * (T * planes * 2 + 1));
-  ftype *h_cs = malloc(sizeof(ftype) * (T * planes * 2 + 1));
-  annb_u32 *h_permb = malloc(sizeof(annb_u32) * T * d_max);
-  annb_u32 *h_pick = malloc(sizeof(annb_u32) * (T * d_short + 1));
-  for (size_t t = 0; t < T; t++) {
+  size_t *own = malloc(sizeof(size_t) * (Tl + 1));             /* global index of owned try j */
+  for (size_t t = 0, j = 0; t < T; t++)
+    if (annb200_dist_try_owner((int)t, R) == rank) own[j++] = t;
+  annb_u32 *h_idx = malloc(sizeof(annb_u32) * (Tl * planes * 2 + 1));
+  ftype *h_cs = malloc(sizeof(ftype) * (Tl * planes * 2 + 1));
+  annb_u32 *h_permb = malloc(sizeof(annb_u32) * (Tl * d_max + 1));
+  annb_u32 *h_pick = malloc(sizeof(annb_u32) * (Tl * d_short + 1));
+  for (size_t j = 0; j < Tl; j++) {
+    const host_transform *f = tf + own[j];
     for (size_t q = 0; q < planes; q++) {
-      h_idx[(t * planes + q) * 2] = (annb_u32)tf[t].ci[q];
-      h_idx[(t * planes + q) * 2 + 1] = (annb_u32)tf[t].cj[q];
+      h_idx[(j * planes + q) * 2] = (annb_u32)f->ci[q];
+      h_idx[(j * planes + q) * 2 + 1] = (annb_u32)f->cj[q];
       /* libm in double on the ftype-rounded angle, then rounded to ftype (ocl2c.h:10)  */
-      h_cs[(t * planes + q) * 2] = cos(tf[t].ang[q]);
-      h_cs[(t * planes + q) * 2 + 1] = sin(tf[t].ang[q]);
+      h_cs[(j * planes + q) * 2] = cos(f->ang[q]);
+      h_cs[(j * planes + q) * 2 + 1] = sin(f->ang[q]);
     }
     for (size_t y = 0; y < d_max; y++) {
-      h_permb[t * d_max + y] = (annb_u32)tf[t].perm_b[y];
-      if (tf[t].perm_ai[y] < d_short) h_pick[t * d_short + tf[t].perm_ai[y]] = (annb_u32)y;
+      h_permb[j * d_max + y] = (annb_u32)f->perm_b[y];
+      if (f->perm_ai[y] < d_short) h_pick[j * d_short + f->perm_ai[y]] = (annb_u32)y;
     }
   }
 
@@ -330,35 +349,35 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   desc.n = n; desc.d = d; desc.d_max = d_max; desc.d_short = d_short;
   desc.rots_before = rots_before; desc.rot_len_before = rot_len_before;
   desc.rots_after = rots_after; desc.rot_len_after = rot_len_after;
-  desc.tries = tries;
+  desc.tries = (int)Tl;
   desc.inv_sqrt2 = 1 / sqrt(2.0);
-  const size_t w = sizeof(ftype);
   const size_t list_bytes = n * k * (4 + w);                   /* one per-try list      */
+  const size_t scratch_bytes = annb_leaf_scratch_bytes(n);
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   free_b += G.arena_bytes;
-  size_t fixed = pad256(n * d * w) * 2 + pad256(d * w) + pad256(T * n * 4) +
+  size_t fixed = pad256(n * d * w) * 2 + pad256(d * w) + pad256(Tl * n * 4 + 4) +
                  pad256(buckets * 4) + pad256((buckets + 1) * 4) + pad256(n * 4) * 2 +
                  pad256(T * 4) + pad256(annb_scan_tmp_bytes(buckets)) +
-                 pad256(T * planes * 2 * 4 + 4) + pad256(T * planes * 2 * w + w) +
-                 pad256(T * d_max * 4) + pad256(T * d_short * 4 + 4) +
+                 pad256(Tl * planes * 2 * 4 + 4) + pad256(Tl * planes * 2 * w + w) +
+                 pad256(Tl * d_max * 4 + 4) + pad256(Tl * d_short * 4 + 4) +
                  pad256(annb_hash_scratch_bytes(&desc)) +
-                 pad256(n * k * 4) * 3 + pad256(n * k * w) * 3 +
-                 pad256(annb_leaf_scratch_bytes(n)) + 8192;
-  size_t group = T;                                            /* lists kept before a merge */
-  while (group > 1 && fixed + group * list_bytes + 512 > free_b * 9 / 10) group--;
-  if ((size_t)k * T < 16) group = T;
+                 pad256(n * k * 4) * 3 + pad256(n * k * w) * 3 + pad256(scratch_bytes) + 8192;
+  if (sharded) fixed += pad256(T * my_rows * k * 4) + pad256(T * my_rows * k * w);
+  size_t group = Tl ? Tl : 1;                                  /* lists kept before a merge */
+  while (!sharded && group > 1 && fixed + group * list_bytes + 512 > free_b * 9 / 10) group--;
+  if ((size_t)k * T < 16) group = Tl ? Tl : 1;
   annh_arena_reserve(fixed + group * list_bytes + 512);
 
   ftype *dX = annh_arena_take(n * d * w), *dXs = annh_arena_take(n * d * w), *dmean = annh_arena_take(d * w);
-  annb_u32 *dhash = annh_arena_take(T * n * 4);
+  annb_u32 *dhash = annh_arena_take(Tl * n * 4 + 4);
   annb_u32 *dcount = annh_arena_take(buckets * 4), *doffset = annh_arena_take((buckets + 1) * 4);
   annb_u32 *dorder_tmp = annh_arena_take(n * 4), *dorder = annh_arena_take(n * 4);
   annb_u32 *dtmax = annh_arena_take(T * 4);
   void *dscan = annh_arena_take(annb_scan_tmp_bytes(buckets));
-  annb_u32 *d_idx = annh_arena_take(T * planes * 2 * 4 + 4);
-  ftype *d_cs = annh_arena_take(T * planes * 2 * w + w);
-  annb_u32 *d_permb = annh_arena_take(T * d_max * 4), *d_pick = annh_arena_take(T * d_short * 4 + 4);
+  annb_u32 *d_idx = annh_arena_take(Tl * planes * 2 * 4 + 4);
+  ftype *d_cs = annh_arena_take(Tl * planes * 2 * w + w);
+  annb_u32 *d_permb = annh_arena_take(Tl * d_max * 4 + 4), *d_pick = annh_arena_take(Tl * d_short * 4 + 4);
   void *dhscratch = annh_arena_take(annb_hash_scratch_bytes(&desc));
   annb_u32 *dl_ids = annh_arena_take(group * n * k * 4);
   ftype *dl_dist = annh_arena_take(group * n * k * w);
@@ -366,20 +385,24 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   ftype *dm_dist = annh_arena_take(n * k * w), *dm_dist2 = annh_arena_take(n * k * w);
   annb_u32 *dout_ids = annh_arena_take(n * k * 4);
   ftype *dout_dist = annh_arena_take(n * k * w);
-  const size_t scratch_bytes = annb_leaf_scratch_bytes(n);
   void *dscratch = annh_arena_take(scratch_bytes);
   int *dstatus = annh_arena_take(sizeof(int));
+  annb_u32 *ds_ids = sharded ? annh_arena_take(T * my_rows * k * 4) : NULL;   /* [T][my_rows][k] */
+  ftype *ds_dist = sharded ? annh_arena_take(T * my_rows * k * w) : NULL;
   CK(cudaMemsetAsync(dstatus, 0, sizeof(int), st));
+  CK(cudaMemsetAsync(dtmax, 0, T * 4, st));
 
-  /* 3. upload                                                                          */
+  /* 3. upload: the whole set, or this rank's rows followed by an all-gather over NVLink   */
   mark(0);
-  CK(cudaMemcpyAsync(dX, points, n * d * w, cudaMemcpyHostToDevice, st));
-  if (planes) {
-    CK(cudaMemcpyAsync(d_idx, h_idx, T * planes * 2 * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d_cs, h_cs, T * planes * 2 * w, cudaMemcpyHostToDevice, st));
+  if (my_rows)
+    CK(cudaMemcpyAsync(dX + row_lo * d, points + row_lo * d, my_rows * d * w, cudaMemcpyHostToDevice, st));
+  if (sharded) annh_dist_allgather_rows(dX, n, d * w, st);
+  if (planes && Tl) {
+    CK(cudaMemcpyAsync(d_idx, h_idx, Tl * planes * 2 * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_cs, h_cs, Tl * planes * 2 * w, cudaMemcpyHostToDevice, st));
   }
-  CK(cudaMemcpyAsync(d_permb, h_permb, T * d_max * 4, cudaMemcpyHostToDevice, st));
-  if (d_short) CK(cudaMemcpyAsync(d_pick, h_pick, T * d_short * 4, cudaMemcpyHostToDevice, st));
+  if (Tl) CK(cudaMemcpyAsync(d_permb, h_permb, Tl * d_max * 4, cudaMemcpyHostToDevice, st));
+  if (d_short && Tl) CK(cudaMemcpyAsync(d_pick, h_pick, Tl * d_short * 4, cudaMemcpyHostToDevice, st));
   desc.plane_idx = d_idx; desc.plane_cs = d_cs; desc.perm_b = d_permb; desc.pick = d_pick;
 
   /* 4. S0 column means (alg.c:367-368); the accumulator borrows the sorted-copy buffer */
@@ -388,9 +411,9 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   for (size_t len = n >> 1; len >> 1; len >>= 1) annb_fold_rows(dXs, dXs, len, d, 0, st);
   annb_scale_means(dXs, n, d, dmean, st);
 
-  /* 5. S1 hashes of every try in one pass over the points                              */
+  /* 5. S1 hashes of every owned try in one pass over the points                         */
   mark(2);
-  annb_hash_points(dX, dmean, &desc, dhash, dhscratch, st);
+  if (Tl) annb_hash_points(dX, dmean, &desc, dhash, dhscratch, st);
   mark(3);
 
   if (save) {
@@ -405,21 +428,26 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
                       d_max, save->bases + t * d_short * d);
   }
 
-  /* 6. per try: S2 bucket tables, S3 k best; merge whenever `group` lists are waiting    */
+  /* 6. per owned try: S2 bucket tables, S3 k best; merge whenever `group` lists wait      */
   const size_t row_len = k * T;
   const int tiny_merge = row_len < 16;
   const size_t prefix = tiny_merge ? row_len : (size_t)1 << floor_log2_sz(row_len);
+  int corner_list = -1, corner_pos = 0;
+  if (!tiny_merge && prefix < row_len) {                         /* DESIGN.md "prefix corner" */
+    corner_list = (int)(prefix / k);
+    corner_pos = (int)(prefix % k);
+  }
   int have_merged = 0;
   size_t *dtable = NULL;
   size_t dtable_cap = 0;
   int admit[64];
-  for (size_t t0 = 0; t0 < T; t0 += group) {
-    size_t g = T - t0 < group ? T - t0 : group;
+  for (size_t j0 = 0; j0 < Tl; j0 += group) {
+    size_t g = Tl - j0 < group ? Tl - j0 : group;
     if (g > 64) annh_fatal("%s", "more than 64 tries per merge group");
     for (size_t j = 0; j < g; j++) {
-      size_t t = t0 + j;
-      annb_build_buckets(dhash + t * n, n, buckets, dcount, doffset, dorder_tmp, dorder,
-                         dtmax + t, dscan, st);
+      size_t t = own[j0 + j];
+      const annb_u32 *hash_t = dhash + (j0 + j) * n;
+      annb_build_buckets(hash_t, n, buckets, dcount, doffset, dorder_tmp, dorder, dtmax + t, dscan, st);
       if (save) {                                  /* padded table for save->which_par[t] */
         annb_u32 tm = 0;
         CK(cudaMemcpyAsync(&tm, dtmax + t, 4, cudaMemcpyDeviceToHost, st));
@@ -436,37 +464,53 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
         CK(cudaMemcpyAsync(save->which_par[t], dtable, cells * sizeof(size_t), cudaMemcpyDeviceToHost, st));
       }
       annb_gather_rows(dX, dorder, n, d, dXs, st);
-      annb_leaf_topk(dXs, dorder, doffset, dhash + t * n, dtmax + t, n, d, d_short, k,
-                     dl_ids + j * n * k, dl_dist + j * n * k, dscratch, dstatus, st);
-      size_t first = k * t;
-      admit[j] = first >= prefix ? 0 : (int)(prefix - first < k ? prefix - first : k);
+      annb_leaf_topk(dXs, dorder, doffset, hash_t, dtmax + t, n, d, d_short, k, dl_ids + j * n * k,
+                     dl_dist + j * n * k, dscratch, dstatus, st);
+      admit[j] = annb200_dist_admit(k, tries, (int)t);
     }
-    {
-      int corner_list = -1, corner_pos = 0;
-      if (!tiny_merge && prefix < row_len && group == T) {      /* DESIGN.md "prefix corner" */
-        corner_list = (int)(prefix / k);
-        corner_pos = (int)(prefix % k);
-      }
-      annb_merge_lists(dl_ids, dl_dist, (int)g, admit, corner_list, corner_pos,
-                       have_merged ? dm_ids : NULL, have_merged ? dm_dist : NULL, n, k,
+    if (!sharded) {
+      int whole = group == Tl;                     /* corner + literal redo need every list */
+      annb_merge_lists(dl_ids, dl_dist, (int)g, admit, whole ? corner_list : -1, corner_pos,
+                       have_merged ? dm_ids : NULL, have_merged ? dm_dist : NULL, n, n, k, whole,
                        dm_ids2, dm_dist2, dscratch, scratch_bytes, dstatus, st);
       annb_u32 *ti = dm_ids; dm_ids = dm_ids2; dm_ids2 = ti;
       ftype *td = dm_dist; dm_dist = dm_dist2; dm_dist2 = td;
+      have_merged = 1;
     }
-    have_merged = 1;
-    if (t0 == 0) mark(4);
+    if (j0 == 0) mark(4);
   }
+  if (Tl == 0) mark(4);
   if (dtable) { CK(cudaStreamSynchronize(st)); CK(cudaFree(dtable)); }
+
+  /* 6b. sharded: every list goes to the owner of its rows, who merges all T of them       */
+  const ftype *own_dist_base = dm_dist;            /* indexed with GLOBAL row numbers       */
+  if (sharded) {
+    annh_dist_exchange_lists(dl_ids, ds_ids, n, k * 4, tries, st);
+    annh_dist_exchange_lists(dl_dist, ds_dist, n, k * w, tries, st);
+    for (size_t t = 0; t < T; t++) admit[t] = annb200_dist_admit(k, tries, (int)t);
+    if (my_rows)
+      annb_merge_lists(ds_ids, ds_dist, tries, admit, corner_list, corner_pos, NULL, NULL, my_rows, n,
+                       k, 1, dm_ids + row_lo * k, dm_dist2, dscratch, scratch_bytes, dstatus, st);
+    annh_dist_allgather_rows(dm_ids, n, k * 4, st);   /* neighbours' lists for supercharging */
+    own_dist_base = dm_dist2 - row_lo * k;
+  }
   mark(5);
 
-  /* 7. S5 supercharging (alg.c:313-327); the graph is the merged lists themselves        */
+  /* 7. S5 supercharging of the owned rows (alg.c:313-327); graph = the merged lists        */
   {
-    int nch = annh_egress_chunks(eg);
+    int nch = full_result && sharded ? 1 : annh_egress_chunks(eg);
     for (int c = 0; c < nch; c++) {
-      size_t r0 = (n * (size_t)c / nch) & ~(size_t)31, r1 = c + 1 == nch ? n : (n * (size_t)(c + 1) / nch) & ~(size_t)31;
-      annb_supercharge(dX, dX, dm_ids, dm_dist, dm_ids, n, d, k, r0, r1, 1, dout_ids + r0 * k,
-                       dists_o ? dout_dist + r0 * k : NULL, dscratch, scratch_bytes, dstatus, st);
-      annh_egress_chunk(eg, r0, r1, dout_ids + r0 * k, dout_dist + r0 * k, st);
+      size_t r0 = row_lo + ((my_rows * (size_t)c / nch) & ~(size_t)31);
+      size_t r1 = c + 1 == nch ? row_hi : row_lo + ((my_rows * (size_t)(c + 1) / nch) & ~(size_t)31);
+      annb_supercharge(dX, dX, dm_ids, own_dist_base, dm_ids, n, d, k, r0, r1, 1, dout_ids + r0 * k,
+                       dout_dist + r0 * k, dscratch, scratch_bytes, dstatus, st);
+      if (!(full_result && sharded))
+        annh_egress_chunk(eg, r0 - row_lo, r1 - row_lo, dout_ids + r0 * k, dout_dist + r0 * k, st);
+    }
+    if (full_result && sharded) {                  /* every rank ends up with all rows      */
+      annh_dist_allgather_rows(dout_ids, n, k * 4, st);
+      annh_dist_allgather_rows(dout_dist, n, k * w, st);
+      annh_egress_chunk(eg, 0, n, dout_ids, dout_dist, st);
     }
   }
   mark(6);
@@ -481,8 +525,8 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   collect_times();
   size_t *result = annh_egress_end(eg, dists_o);
   if (h_status) annh_fatal("%s", "scratch too small for a literal candidate row (extremely unbalanced buckets)");
-  for (size_t t = 0; t < T; t++)
-    if ((d_short + 1) * (size_t)h_tmax[t] < 16)
+  for (size_t j = 0; j < Tl; j++)
+    if ((d_short + 1) * (size_t)h_tmax[own[j]] < 16)
       annh_fatal("%s", "candidate rows shorter than 16 slots (n far too small for this k)");
   free(h_tmax);
 
@@ -492,7 +536,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
     memcpy(result, save->graph, sizeof(size_t) * n * k);
   }
   for (size_t t = 0; t < T; t++) free_transform(tf + t);
-  free(tf); free(h_idx); free(h_cs); free(h_permb); free(h_pick);
+  free(tf); free(own); free(h_idx); free(h_cs); free(h_permb); free(h_pick);
   return result;
 }
 

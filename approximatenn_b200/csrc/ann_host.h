@@ -42,6 +42,14 @@ void annh_egress_chunk(annh_egress *e, size_t r0, size_t r1, const void *dev_ids
 size_t *annh_egress_end(annh_egress *e, ftype **dists_o);
 void annh_egress_release(void);
 
+/* sharded execution (ann_dist.c); world == 1 unless annb200_dist_init() was called          */
+int annh_dist_rank(void);
+int annh_dist_world(void);
+int annh_dist_gather_results(void);
+void annh_dist_allgather_rows(void *base, size_t n, size_t row_bytes, void *stream);
+void annh_dist_exchange_lists(const void *local, void *slice, size_t n, size_t row_bytes, int tries,
+                              void *stream);
+
 /* drops any device-resident copy of `save` kept for query_gpu (called by free_save)      */
 void annh_forget_save(const save_t *save);
 

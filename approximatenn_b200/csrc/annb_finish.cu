@@ -28,12 +28,11 @@ template <int R>
 __global__ void __launch_bounds__(256)
 merge_lists_kernel(const u32 *__restrict__ lists_ids, const FT *__restrict__ lists_dist,
                    MergeArgs a, const u32 *__restrict__ prev_ids, const FT *__restrict__ prev_dist,
-                   size_t n, int k, u32 *__restrict__ out_ids, FT *__restrict__ out_dist,
-                   unsigned char *__restrict__ tie_flags) {
+                   size_t n, u32 sentinel, int k, u32 *__restrict__ out_ids,
+                   FT *__restrict__ out_dist, unsigned char *__restrict__ tie_flags) {
   const int lane = threadIdx.x & 31;
   size_t x = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (x >= n) return;
-  const u32 sentinel = (u32)n;
   WarpList<R> best;
   best.clear(sentinel);
   FT tau = ft_inf();
@@ -120,7 +119,7 @@ merge_literal_kernel(const u32 *__restrict__ lists_ids, const FT *__restrict__ l
 extern "C" void annb_merge_lists(const u32 *lists_ids, const FT *lists_dist, int n_lists,
                                  const int *host_admit, int corner_list, int corner_pos,
                                  const u32 *merged_in_ids, const FT *merged_in_dist, size_t n,
-                                 size_t k, u32 *merged_ids, FT *merged_dist, void *scratch,
+                                 size_t sentinel_n, size_t k, int every_list, u32 *merged_ids, FT *merged_dist, void *scratch,
                                  size_t scratch_bytes, int *status, annb_stream stream) {
   int regs = list_regs(k);
   if (!regs) fatal_config("k > 256");
@@ -128,7 +127,7 @@ extern "C" void annb_merge_lists(const u32 *lists_ids, const FT *lists_dist, int
   unsigned char *flags = (unsigned char *)scratch;
   unsigned char *slabs = (unsigned char *)(((uintptr_t)(flags + n) + 255) & ~(uintptr_t)255);
   size_t slab_bytes = scratch_bytes > n + 512 ? scratch_bytes - n - 512 : 0;
-  const bool whole_row = merged_in_ids == NULL;       // the literal redo needs every list
+  const bool whole_row = merged_in_ids == NULL && every_list;   // the literal redo needs every list of the row
   if ((size_t)n_lists * k < 16) {
     if (!whole_row) fatal_config("rows shorter than 16 slots cannot be merged incrementally");
     merge_literal_kernel<<<148 * 2, 256, 0, stream>>>(lists_ids, lists_dist, n_lists, n, (int)k, merged_ids, merged_dist, NULL, slabs, slab_bytes, status);
@@ -144,10 +143,10 @@ extern "C" void annb_merge_lists(const u32 *lists_ids, const FT *lists_dist, int
   unsigned char *f = whole_row ? flags : NULL;
   dim3 block(256), grid(grid_for(n * 32, 256));
   switch (regs) {
-    case 1: merge_lists_kernel<1><<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, merged_in_ids, merged_in_dist, n, (int)k, merged_ids, merged_dist, f); break;
-    case 2: merge_lists_kernel<2><<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, merged_in_ids, merged_in_dist, n, (int)k, merged_ids, merged_dist, f); break;
-    case 4: merge_lists_kernel<4><<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, merged_in_ids, merged_in_dist, n, (int)k, merged_ids, merged_dist, f); break;
-    default: merge_lists_kernel<8><<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, merged_in_ids, merged_in_dist, n, (int)k, merged_ids, merged_dist, f); break;
+    case 1: merge_lists_kernel<1><<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, merged_in_ids, merged_in_dist, n, (u32)sentinel_n, (int)k, merged_ids, merged_dist, f); break;
+    case 2: merge_lists_kernel<2><<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, merged_in_ids, merged_in_dist, n, (u32)sentinel_n, (int)k, merged_ids, merged_dist, f); break;
+    case 4: merge_lists_kernel<4><<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, merged_in_ids, merged_in_dist, n, (u32)sentinel_n, (int)k, merged_ids, merged_dist, f); break;
+    default: merge_lists_kernel<8><<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, merged_in_ids, merged_in_dist, n, (u32)sentinel_n, (int)k, merged_ids, merged_dist, f); break;
   }
   LAUNCH_CHECK("merge_lists");
   if (whole_row) {

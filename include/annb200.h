@@ -102,15 +102,18 @@ void annb_leaf_topk(const ftype *sorted_points, const annb_u32 *order, const ann
  * the sorted prefix (k, or fewer for the try that straddles 2^floor(log2(k*tries))).
  * corner_list/corner_pos: the list entry sitting in the first slot OUTSIDE the prefix
  * (or corner_list < 0 when the row length is a power of two) — see DESIGN.md "prefix
- * corner".  merged: [n][k].  If merged_in != NULL it is treated as one more, fully
- * admitted list (running merge; no literal redo is possible then).  Rows shorter than 16
+ * corner".  merged: [n][k]; n = rows merged here, sentinel_n = size of the whole point set
+ * (they differ when a rank merges only its row slice).  If merged_in != NULL it is treated as one more, fully
+ * admitted list (running merge).  every_list != 0 says the call sees ALL lists of the row;
+ * only then can tied rows be redone literally.  Rows shorter than 16
  * slots (k*n_lists < 16) are always done literally.
  * scratch: at least n + 512 bytes plus room for literal rows (64 MB is plenty).           */
 void annb_merge_lists(const annb_u32 *lists_ids, const ftype *lists_dist, int n_lists,
                       const int *host_admit, int corner_list, int corner_pos,
                       const annb_u32 *merged_in_ids, const ftype *merged_in_dist,
-                      size_t n, size_t k, annb_u32 *merged_ids, ftype *merged_dist,
-                      void *scratch, size_t scratch_bytes, int *status, annb_stream stream);
+                      size_t n, size_t sentinel_n, size_t k, int every_list, annb_u32 *merged_ids,
+                      ftype *merged_dist, void *scratch, size_t scratch_bytes, int *status,
+                      annb_stream stream);
 
 /* ---- S5: supercharging (supercharge + compdists + second sort_and_uniq, alg.c:313-335) --
  * For each query row x in [row_begin, row_end): candidates = own list ++ the lists of its

@@ -1,0 +1,66 @@
+"""torchrun worker for tests/test_gpu_multi.py: sharded precomp_gpu vs the single-process
+CPU oracle.  Every rank checks the rows it owns (and the full result in gather mode)."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+from approximatenn_b200 import dist as adist  # noqa: E402
+from approximatenn_b200.api import _libc, _view, gpu_backend, srandom  # noqa: E402
+
+
+def run_case(gpu, dtype, n, d, k, tries, seed, gather):
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rng = np.random.default_rng(seed)
+    pts = rng.standard_normal((n, d)).astype(dtype)
+    want = oracle.restatement(dtype).precomp(pts, k, tries, seed=seed)
+    gpu.lib.annb200_dist_gather(1 if gather else 0)
+    lo, hi = (0, n) if gather else adist.row_slice(gpu.lib, n, rank, world)
+    dptr = ctypes.c_void_p()
+    srandom(seed)
+    ids = gpu.precomp_raw(n, k, d, pts.ctypes.data, tries, 6, 1, 1, 1, None, ctypes.byref(dptr))
+    got_ids = _view(ids, (hi - lo, k), np.uint64).copy()
+    got_d = _view(dptr, (hi - lo, k), dtype).copy()
+    _libc.free(ids); _libc.free(dptr)
+    ok = np.array_equal(got_ids, want.ids[lo:hi]) and np.array_equal(
+        got_d.view(np.uint8), np.ascontiguousarray(want.dists[lo:hi]).view(np.uint8))
+    print(f"rank {rank}/{world} {np.dtype(dtype).name} n={n} d={d} k={k} T={tries} gather={gather} "
+          f"rows [{lo},{hi}) {'OK' if ok else 'MISMATCH'}", flush=True)
+    return ok
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ["ANN_B200_DEVICE"] = str(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    gpus = {}
+    for dtype in (np.float32, np.float64):
+        gpus[dtype] = gpu_backend(dtype)
+        adist.init_from_torch(gpus[dtype].lib)
+    cases = [
+        (np.float32, 8192, 64, 16, 8, 401, False),
+        (np.float32, 8192, 64, 16, 8, 401, True),
+        (np.float32, 5003, 16, 10, 10, 402, False),     # k*T = 100: prefix corner, uneven try split
+        (np.float64, 4096, 32, 16, 5, 403, False),      # more ranks than some ranks have tries
+        (np.float32, 3000, 20, 10, 3, 404, True),
+    ]
+    for dtype, n, d, k, tries, seed, gather in cases:
+        ok &= run_case(gpus[dtype], dtype, n, d, k, tries, seed, gather)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    for g in gpus.values():
+        g.lib.annb200_dist_shutdown()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
