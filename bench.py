@@ -146,6 +146,7 @@ def workload_config(cfg, name, gpus):
     return {"workload": f"BASELINE {name}: n={n} d={d} k={k} {np.dtype(dtype).name}, {tries} tries + supercharge, "
                         f"rotations {ROT}, iid N(0,1) points",
             "n": n, "d": d, "k": k, "tries": tries, "gpus": gpus,
+            "parallelism": "1 GPU" if gpus == 1 else f"tries sharded over {gpus} ranks, rows of merge+supercharge sliced, NCCL all-to-all/all-gather",
             "l2": "inputs (n*d*4 B = %.0f MB) exceed the 126 MB L2; no flush needed" % (n * d * np.dtype(dtype).itemsize / 1e6)}
 
 
@@ -182,6 +183,12 @@ def main():
     gpu = gpu_backend(dtype)
     gpu.lib.gpu_init()
     gpu.lib.annh_set_timing(1)
+    if world > 1:
+        # tries are sharded across ranks inside the library (csrc/ann_dist.c); torch.distributed
+        # only carries NCCL's unique id.  Every rank passes the same points and the same seed and
+        # gets back the rows it owns.
+        from approximatenn_b200 import dist as adist
+        adist.init_from_torch(gpu.lib, gather_full=False)
 
     # pinned host input: the buffer the caller hands to precomp_gpu
     host = torch.empty((n, d), dtype=torch.float32 if dtype == np.float32 else torch.float64,
@@ -233,9 +240,10 @@ def main():
     mean_stage = {k_: statistics.mean(s[k_] for s in stages) for k_ in stages[0]}
     peak, peak_src = measured_peaks()
     # dominant HBM-bound kernel: supercharge.  Algorithmic bytes per launch:
-    # n*(P2-k) gathered rows of (4 + d*w) B, + own lists in, + size_t ids and dists out.
+    # rows*(P2-k) gathered vectors of (4 + d*w) B, + own lists in, + ids and dists out.
     P2 = 1 << ((k * (k + 1)).bit_length() - 1)
-    sc_bytes = n * (P2 - k) * (4 + d * w) + n * k * (4 + w) + n * k * (8 + w)
+    rows = n / world                      # supercharge rows per rank
+    sc_bytes = rows * (P2 - k) * (4 + d * w) + rows * k * (4 + w) + rows * k * (4 + w)
     sc_s = mean_stage["supercharge"] / 1e3
     roofline = {"kernel": "supercharge_kernel", "bound": "hbm", "achieved": sc_bytes / sc_s / 1e9,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s",
@@ -248,7 +256,7 @@ def main():
             "dtype": "f32" if dtype == np.float32 else "f64", "data": "synthetic",
             "config": workload_config(cfg, args.config, world),
             "e2e": {"value": n * args.steps / wall, "unit": "points/s",
-                    "h2d_bytes_per_step": n * d * w, "d2h_bytes_per_step": n * k * (8 + w),
+                    "h2d_bytes_per_step": n * d * w, "d2h_bytes_per_step": n * k * (4 + w),
                     "ms_per_step": 1e3 * wall / args.steps},
             "gpu_launches": launches, "stage_ms": mean_stage, "roofline": roofline,
             "clocks": sampler.summary()}

@@ -78,6 +78,10 @@ def _declare_stage_api(b: Backend) -> None:
     L.orc_state_projection.restype = None
     L.orc_try_lists.argtypes = [vp, vp, ctypes.c_int, vp, sz, vp, vp]
     L.orc_try_lists.restype = None
+    L.orc_merge_rows.argtypes = [vp, vp, sz, sz]
+    L.orc_merge_rows.restype = None
+    L.orc_supercharge_rows.argtypes = [sz, sz, sz, vp, vp, sz, sz, vp, vp, sz, vp, sz, ctypes.c_int, vp, vp]
+    L.orc_supercharge_rows.restype = None
     L.orc_sampled_cost.argtypes = [sz, sz, sz, vp, ctypes.c_int, sz, sz, sz, sz, vp, sz,
                                    ctypes.POINTER(ctypes.c_double)]
     L.orc_sampled_cost.restype = sz
@@ -159,3 +163,25 @@ def sampled_cost(b: Backend, points, k, tries, sample, rots_before=6, rot_len_be
                                   rots_before, rot_len_before, rots_after, rot_len_after,
                                   sample.ctypes.data, len(sample), secs)
     return {"prepare_s": secs[0], "row_s": secs[1], "supercharge_s": secs[2], "rows": rows}
+
+
+def merge_rows(b: Backend, ids, key):
+    """In place: the reference's sort / kill duplicates / sort on every row (alg.c:312)."""
+    assert ids.dtype == np.uint64 and ids.flags.c_contiguous and key.flags.c_contiguous
+    b.lib.orc_merge_rows(ids.ctypes.data, key.ctypes.data, ids.shape[0], ids.shape[1])
+
+
+def supercharge_rows(b: Backend, points, queries, r0, r1, own_ids, own_key, graph, k, exclude_self=True):
+    """alg.c:313-335 for query rows [r0, r1); own_* are indexed by x - r0, graph by point id."""
+    pts = np.ascontiguousarray(points, dtype=b.dtype)
+    qs = pts if queries is points else np.ascontiguousarray(queries, dtype=b.dtype)
+    own_ids = np.ascontiguousarray(own_ids, dtype=np.uint64)
+    own_key = np.ascontiguousarray(own_key, dtype=b.dtype)
+    graph = np.ascontiguousarray(graph, dtype=np.uint64)
+    out_i = np.empty((r1 - r0, k), dtype=np.uint64)
+    out_k = np.empty((r1 - r0, k), dtype=b.dtype)
+    b.lib.orc_supercharge_rows(pts.shape[0], k, pts.shape[1], qs.ctypes.data, pts.ctypes.data, r0, r1,
+                               own_ids.ctypes.data, own_key.ctypes.data, own_ids.shape[1],
+                               graph.ctypes.data, graph.shape[1], 1 if exclude_self else 0,
+                               out_i.ctypes.data, out_k.ctypes.data)
+    return out_i, out_k

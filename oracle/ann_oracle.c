@@ -638,3 +638,36 @@ size_t orc_sampled_cost(size_t n, size_t k, size_t d, const ftype *points, int t
   orc_release(s, 0);
   return rows;
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* the two halves of det_results as separate entry points (used by the sharding tests)   */
+
+/* first sort_and_uniq of det_results (alg.c:312) on `rows` rows of `len` slots, in place  */
+void orc_merge_rows(size_t *ids, ftype *key, size_t rows, size_t len) {
+  for (size_t x = 0; x < rows; x++) sort_and_uniq_row(ids + x * len, key + x * len, len);
+}
+
+/* supercharge + compdists + second sort_and_uniq (alg.c:313-335) for query rows
+ * [r0, r1): own lists are rows of own_ids/own_key (stride own_stride, indexed by x - r0),
+ * neighbour lists are rows of `graph` (stride gstride, indexed by point id).               */
+void orc_supercharge_rows(size_t n, size_t k, size_t d, const ftype *queries, const ftype *points,
+                          size_t r0, size_t r1, const size_t *own_ids, const ftype *own_key,
+                          size_t own_stride, const size_t *graph, size_t gstride, int exclude_self,
+                          size_t *ids_out, ftype *key_out) {
+  size_t wide = k * (k + 1);
+  row_buf tmp = {0};
+  row_reserve(&tmp, wide, d);
+  for (size_t x = r0; x < r1; x++) {
+    const size_t *own = own_ids + (x - r0) * own_stride;
+    memcpy(tmp.ids, own, sizeof(size_t) * k);
+    memcpy(tmp.key, own_key + (x - r0) * own_stride, sizeof(ftype) * k);
+    for (size_t j = 0; j < k; j++)
+      for (size_t z = 0; z < k; z++)
+        tmp.ids[(j + 1) * k + z] = own[j] < n ? graph[own[j] * gstride + z] : n;
+    row_distances(&tmp, k, wide, queries + x * d, exclude_self ? x : n, points, n, d);
+    sort_and_uniq_row(tmp.ids, tmp.key, wide);
+    memcpy(ids_out + (x - r0) * k, tmp.ids, sizeof(size_t) * k);
+    memcpy(key_out + (x - r0) * k, tmp.key, sizeof(ftype) * k);
+  }
+  row_release(&tmp);
+}
