@@ -276,6 +276,27 @@ static void collect_times(void) {
   }
 }
 
+/* host wall-clock checkpoints (ANN_B200_HOSTPROF=1 prints them to stderr)                */
+#include <time.h>
+static double now_ms(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+static int hostprof(void) {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("ANN_B200_HOSTPROF"); v = e && *e && *e != '0'; }
+  return v;
+}
+#define HP(label)                                                                       \
+  do {                                                                                  \
+    if (hostprof()) {                                                                   \
+      double t_ = now_ms();                                                             \
+      fprintf(stderr, "[hostprof r%d] %-28s +%8.3f ms (total %8.3f)\n", annh_dist_rank(), label, t_ - hp_last, t_ - hp_start); \
+      hp_last = t_;                                                                     \
+    }                                                                                   \
+  } while (0)
+
 /* ------------------------------------------------------------------------------------ */
 /* precomp_gpu                                                                            */
 
@@ -293,11 +314,13 @@ static void validate(size_t n, size_t k, size_t d, int tries, size_t len_b, size
 size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries,
                     size_t rots_before, size_t rot_len_before, size_t rots_after,
                     size_t rot_len_after, save_t *save, ftype **dists_o) {
+  double hp_start = now_ms(), hp_last = hp_start;
   gpu_init();
   CK(cudaSetDevice(G.device));
   size_t d_short, d_max;
   annh_params(n, k, d, &d_short, &d_max);
   validate(n, k, d, tries, rot_len_before, rot_len_after, d_short);
+  HP("init");
   const size_t T = (size_t)tries, buckets = (size_t)1 << d_short;
   const size_t planes = rots_before * rot_len_before + rots_after * rot_len_after;
   const size_t w = sizeof(ftype);
@@ -317,6 +340,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   const size_t out_rows = full_result ? n : my_rows;
   annh_egress *eg = annh_egress_begin(out_rows, k, dists_o != NULL, G.device);
 
+  HP("egress_begin");
   /* 1. transforms: ALL tries are drawn before any compute (alg.c:388-392), on every rank   */
   host_transform *tf = malloc(sizeof(host_transform) * T);
   for (size_t t = 0; t < T; t++)
@@ -343,6 +367,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
     }
   }
 
+  HP("transforms");
   /* 2. device memory plan                                                              */
   annb_transform_desc desc;
   memset(&desc, 0, sizeof desc);
@@ -392,6 +417,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   CK(cudaMemsetAsync(dstatus, 0, sizeof(int), st));
   CK(cudaMemsetAsync(dtmax, 0, T * 4, st));
 
+  HP("arena");
   /* 3. upload: the whole set, or this rank's rows followed by an all-gather over NVLink   */
   mark(0);
   if (my_rows)
@@ -405,6 +431,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   if (d_short && Tl) CK(cudaMemcpyAsync(d_pick, h_pick, Tl * d_short * 4, cudaMemcpyHostToDevice, st));
   desc.plane_idx = d_idx; desc.plane_cs = d_cs; desc.perm_b = d_permb; desc.pick = d_pick;
 
+  HP("upload enqueued");
   /* 4. S0 column means (alg.c:367-368); the accumulator borrows the sorted-copy buffer */
   mark(1);
   annb_fold_rows(dX, dXs, n, d, 1, st);
@@ -482,6 +509,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   if (Tl == 0) mark(4);
   if (dtable) { CK(cudaStreamSynchronize(st)); CK(cudaFree(dtable)); }
 
+  HP("tries enqueued");
   /* 6b. sharded: every list goes to the owner of its rows, who merges all T of them       */
   const ftype *own_dist_base = dm_dist;            /* indexed with GLOBAL row numbers       */
   if (sharded) {
@@ -515,6 +543,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   }
   mark(6);
 
+  HP("supercharge enqueued");
   /* 8. results: the egress threads are already widening the first chunks                 */
   annb_u32 *h_tmax = malloc(4 * T);
   int h_status = 0;
@@ -522,8 +551,10 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   CK(cudaMemcpyAsync(&h_status, dstatus, sizeof(int), cudaMemcpyDeviceToHost, st));
   mark(7);
   CK(cudaStreamSynchronize(st));
+  HP("stream drained");
   collect_times();
   size_t *result = annh_egress_end(eg, dists_o);
+  HP("egress_end");
   if (h_status) annh_fatal("%s", "scratch too small for a literal candidate row (extremely unbalanced buckets)");
   for (size_t j = 0; j < Tl; j++)
     if ((d_short + 1) * (size_t)h_tmax[own[j]] < 16)

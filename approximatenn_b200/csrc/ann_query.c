@@ -144,7 +144,7 @@ size_t *query_gpu(const save_t *save, const ftype *points, size_t ycnt, const ft
     build_index(save, points, fp);
 
   annh_egress *eg = annh_egress_begin(ycnt, k, dists_o != NULL, annh_device());
-  const size_t scratch_bytes = ycnt + 512 + ((size_t)64 << 20);
+  const size_t scratch_bytes = ycnt * 4 + 1024 + ((size_t)64 << 20);
   size_t need = (ycnt * d * w + 256) + (T * ycnt * 4 + 256) + 2 * (ycnt * k * 4 + 256) +
                 2 * (ycnt * k * w + 256) + scratch_bytes + 4096;
   annh_arena_reserve(need);

@@ -242,19 +242,48 @@ __device__ __forceinline__ int floor_log2_u(unsigned long long v) { return 63 - 
 
 
 // =====================================================================================
-// the reference's sorting network and duplicate rule, literally, one warp per row
+// rows to redo literally + the reference's sorting network, one CTA per row
 // =====================================================================================
+// Fast kernels append the rows in which an exact tie could matter to a TieList; the literal
+// kernels walk that list (or all rows when rows == NULL: rows shorter than 16 slots).
+
+struct TieList {
+  u32 *count;     // [1]
+  u32 *rows;      // [capacity] or NULL = every row
+};
+
+__device__ __forceinline__ void tie_report(const TieList &t, u32 row) {
+  u32 i = atomicAdd(t.count, 1u);
+  t.rows[i] = row;
+}
+
+// scratch = [count | rows[cap] | slabs ...]; carved identically on host and device
+struct LiteralScratch {
+  TieList list;
+  unsigned char *slabs;
+  size_t slab_bytes;
+};
+static inline LiteralScratch carve_literal_scratch(void *scratch, size_t scratch_bytes, size_t cap_rows) {
+  LiteralScratch L;
+  unsigned char *p = (unsigned char *)scratch;
+  L.list.count = (u32 *)p;
+  L.list.rows = (u32 *)(p + 256);
+  size_t used = (256 + cap_rows * sizeof(u32) + 255) & ~(size_t)255;
+  L.slabs = p + used;
+  L.slab_bytes = scratch_bytes > used ? scratch_bytes - used : 0;
+  return L;
+}
+
 // compute.cl:181-217 + alg.c:137-144,224-230.  ids/key may live in shared or global memory.
-// Every (stage, sub) step is a set of disjoint compare-exchanges, so the lanes share them.
+// Every (stage, sub) step is a set of disjoint compare-exchanges shared by the CTA's threads.
 // For len < 16 the network degenerates exactly as the reference's does (one work item of 8
 // comparators guarded by pb < len).
-
-__device__ __forceinline__ void warp_network_sort(u32 *ids, FT *key, int len, int lane) {
+__device__ __forceinline__ void block_network_sort(u32 *ids, FT *key, int len) {
   const int lk = floor_log2_u((unsigned long long)len);
   const int comps = 8 << (lk > 4 ? lk - 4 : 0);
   for (int stage = 0; stage < lk; stage++)
     for (int sub = stage; sub >= 0; sub--) {
-      for (int w = lane; w < comps; w += 32) {
+      for (int w = threadIdx.x; w < comps; w += blockDim.x) {
         int hi = (w >> sub) << sub, lo = w ^ hi;
         int pa = (hi << 1) | lo;
         if (sub == stage) lo = (1 << sub) - lo - 1;
@@ -268,16 +297,46 @@ __device__ __forceinline__ void warp_network_sort(u32 *ids, FT *key, int len, in
           }
         }
       }
-      __syncwarp();
+      __syncthreads();
     }
 }
 
-__device__ __forceinline__ void warp_sort_and_uniq(u32 *ids, FT *key, int len, int lane) {
-  warp_network_sort(ids, key, len, lane);
-  for (int y = lane; y + 1 < len; y += 32)
+__device__ __forceinline__ void block_sort_and_uniq(u32 *ids, FT *key, int len) {
+  block_network_sort(ids, key, len);
+  for (int y = threadIdx.x; y + 1 < len; y += blockDim.x)
     if (ids[y] == ids[y + 1]) key[y] = ft_inf();
-  __syncwarp();
-  warp_network_sort(ids, key, len, lane);
+  __syncthreads();
+  block_network_sort(ids, key, len);
+}
+
+// Distances from one query row to `count` rows given by row_of(i), written by key_at(i):
+// the CTA's warps share the rows, each warp keeps 8 candidate rows in flight.
+template <int E, typename RowOf, typename Emit>
+__device__ __forceinline__ void block_row_distances(const FT *__restrict__ qrow, const FT *__restrict__ base,
+                                                    int d, u32 count, FT *tmp, RowOf row_of, Emit emit) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (E) {
+    WarpRow<(E ? E : 1)> qr;
+    qr.load(qrow, lane, d);
+    for (u32 i0 = wib * 8; i0 < count; i0 += nw * 8) {
+      WarpRow<(E ? E : 1)> cr[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        u32 i = min(i0 + u, count - 1);
+        cr[u].load(base + row_of(i) * (size_t)d, lane, d);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        FT dist = __shfl_sync(FULL, warp_sqdist<(E ? E : 1)>(qr, cr[u], d), 0);
+        if (lane == 0 && i0 + u < count) emit(i0 + u, dist);
+      }
+    }
+  } else {
+    for (u32 i = wib; i < count; i += nw) {
+      FT dist = generic_sqdist(qrow, base + row_of(i) * (size_t)d, d, tmp, lane);
+      if (lane == 0) emit(i, dist);
+    }
+  }
 }
 
 // exact squared distance between two global rows, result warp-uniform; E as in row_mode()

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256)
 merge_lists_kernel(const u32 *__restrict__ lists_ids, const FT *__restrict__ lists_dist,
                    MergeArgs a, const u32 *__restrict__ prev_ids, const FT *__restrict__ prev_dist,
                    size_t n, u32 sentinel, int k, u32 *__restrict__ out_ids,
-                   FT *__restrict__ out_dist, unsigned char *__restrict__ tie_flags) {
+                   FT *__restrict__ out_dist, TieList ties) {
   const int lane = threadIdx.x & 31;
   size_t x = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (x >= n) return;
@@ -70,49 +70,43 @@ merge_lists_kernel(const u32 *__restrict__ lists_ids, const FT *__restrict__ lis
       out_dist[x * (size_t)k + p] = best.v[rr];
     }
   }
-  if (tie && tie_flags && lane == 0) tie_flags[x] = 1;
+  if (tie && ties.rows && lane == 0) tie_report(ties, (u32)x);
 }
 
 // Literal row: the n_lists lists of a point side by side (k*n_lists slots), the reference's
-// network, first k slots out.  tie_flags == NULL: every row (rows shorter than 16 slots).
+// network, first k slots out.  One CTA per reported row (ties.rows == NULL: every row — rows
+// shorter than 16 slots).
 __global__ void __launch_bounds__(256)
 merge_literal_kernel(const u32 *__restrict__ lists_ids, const FT *__restrict__ lists_dist,
                      int n_lists, size_t n, int k, u32 *__restrict__ out_ids,
-                     FT *__restrict__ out_dist, const unsigned char *__restrict__ tie_flags,
-                     unsigned char *scratch, size_t scratch_bytes, int *status) {
-  const int lane = threadIdx.x & 31;
-  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+                     FT *__restrict__ out_dist, TieList ties, unsigned char *slabs,
+                     size_t slab_bytes, int *status) {
+  const int tid = threadIdx.x;
+  const u32 total = ties.rows ? *ties.count : (u32)n;
+  if (total == 0) return;
   const int len = n_lists * k;
   const size_t slab = ((size_t)len * (sizeof(u32) + sizeof(FT)) + 15) & ~(size_t)15;
-  const size_t slabs = scratch_bytes / slab;
-  if (slabs == 0) { if (warp == 0 && lane == 0) *status = 1; return; }
-  const size_t workers = slabs < nwarps ? slabs : nwarps;
-  if (warp >= workers) return;
-  FT *key = reinterpret_cast<FT *>(scratch + warp * slab);
+  const size_t fit = slab_bytes / slab;
+  if (fit == 0) { if (blockIdx.x == 0 && tid == 0) *status = 1; return; }
+  const u32 workers = (u32)(fit < gridDim.x ? fit : gridDim.x);
+  if (blockIdx.x >= workers) return;
+  if (blockIdx.x == 0 && tid == 0) atomicAdd(&finish_literal_rows_dev[0], (unsigned long long)total);
+  FT *key = reinterpret_cast<FT *>(slabs + (size_t)blockIdx.x * slab);
   u32 *ids = reinterpret_cast<u32 *>(key + len);
-
-  for (size_t base = warp * 32; base < n; base += workers * 32) {
-    size_t p = base + lane;
-    unsigned flagged = __ballot_sync(FULL, p < n && (!tie_flags || tie_flags[p]));
-    while (flagged) {
-      int src = __ffs(flagged) - 1;
-      flagged &= flagged - 1;
-      const size_t x = base + src;
-      if (lane == 0) atomicAdd(&finish_literal_rows_dev[0], 1ull);
-      for (int e = lane; e < len; e += 32) {
-        int t = e / k, z = e - t * k;
-        ids[e] = lists_ids[((size_t)t * n + x) * k + z];
-        key[e] = lists_dist[((size_t)t * n + x) * k + z];
-      }
-      __syncwarp();
-      warp_sort_and_uniq(ids, key, len, lane);
-      for (int i = lane; i < k; i += 32) {
-        out_ids[x * (size_t)k + i] = ids[i];
-        out_dist[x * (size_t)k + i] = key[i];
-      }
-      __syncwarp();
+  for (u32 it = blockIdx.x; it < total; it += workers) {
+    const size_t x = ties.rows ? ties.rows[it] : it;
+    for (int e = tid; e < len; e += blockDim.x) {
+      int t = e / k, z = e - t * k;
+      ids[e] = lists_ids[((size_t)t * n + x) * k + z];
+      key[e] = lists_dist[((size_t)t * n + x) * k + z];
     }
+    __syncthreads();
+    block_sort_and_uniq(ids, key, len);
+    for (int i = tid; i < k; i += blockDim.x) {
+      out_ids[x * (size_t)k + i] = ids[i];
+      out_dist[x * (size_t)k + i] = key[i];
+    }
+    __syncthreads();
   }
 }
 
@@ -124,13 +118,12 @@ extern "C" void annb_merge_lists(const u32 *lists_ids, const FT *lists_dist, int
   int regs = list_regs(k);
   if (!regs) fatal_config("k > 256");
   if (n_lists > 64) fatal_config("more than 64 lists per merge call");
-  unsigned char *flags = (unsigned char *)scratch;
-  unsigned char *slabs = (unsigned char *)(((uintptr_t)(flags + n) + 255) & ~(uintptr_t)255);
-  size_t slab_bytes = scratch_bytes > n + 512 ? scratch_bytes - n - 512 : 0;
+  LiteralScratch ls = carve_literal_scratch(scratch, scratch_bytes, n);
   const bool whole_row = merged_in_ids == NULL && every_list;   // the literal redo needs every list of the row
+  TieList all_rows = {ls.list.count, NULL};
   if ((size_t)n_lists * k < 16) {
     if (!whole_row) fatal_config("rows shorter than 16 slots cannot be merged incrementally");
-    merge_literal_kernel<<<148 * 2, 256, 0, stream>>>(lists_ids, lists_dist, n_lists, n, (int)k, merged_ids, merged_dist, NULL, slabs, slab_bytes, status);
+    merge_literal_kernel<<<148 * 4, 256, 0, stream>>>(lists_ids, lists_dist, n_lists, n, (int)k, merged_ids, merged_dist, all_rows, ls.slabs, ls.slab_bytes, status);
     LAUNCH_CHECK("merge_literal");
     return;
   }
@@ -139,8 +132,8 @@ extern "C" void annb_merge_lists(const u32 *lists_ids, const FT *lists_dist, int
   for (int i = 0; i < n_lists; i++) a.admit[i] = host_admit[i];
   a.corner_list = corner_list;
   a.corner_pos = corner_pos;
-  if (whole_row) cudaMemsetAsync(flags, 0, n, stream);
-  unsigned char *f = whole_row ? flags : NULL;
+  if (whole_row) cudaMemsetAsync(ls.list.count, 0, sizeof(u32), stream);
+  TieList f = whole_row ? ls.list : all_rows;        // rows == NULL: ties are not recorded
   dim3 block(256), grid(grid_for(n * 32, 256));
   switch (regs) {
     case 1: merge_lists_kernel<1><<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, merged_in_ids, merged_in_dist, n, (u32)sentinel_n, (int)k, merged_ids, merged_dist, f); break;
@@ -150,7 +143,7 @@ extern "C" void annb_merge_lists(const u32 *lists_ids, const FT *lists_dist, int
   }
   LAUNCH_CHECK("merge_lists");
   if (whole_row) {
-    merge_literal_kernel<<<148, 256, 0, stream>>>(lists_ids, lists_dist, n_lists, n, (int)k, merged_ids, merged_dist, flags, slabs, slab_bytes, status);
+    merge_literal_kernel<<<148 * 2, 256, 0, stream>>>(lists_ids, lists_dist, n_lists, n, (int)k, merged_ids, merged_dist, ls.list, ls.slabs, ls.slab_bytes, status);
     LAUNCH_CHECK("merge_literal");
   }
 }
@@ -168,7 +161,7 @@ supercharge_kernel(const FT *__restrict__ queries, const FT *__restrict__ points
                    const u32 *__restrict__ own_ids, const FT *__restrict__ own_dist,
                    const u32 *__restrict__ graph, size_t n, int d, int k, size_t row_begin,
                    size_t row_end, int exclude_self, u32 *__restrict__ out_ids,
-                   FT *__restrict__ out_dist, unsigned char *__restrict__ tie_flags) {
+                   FT *__restrict__ out_dist, TieList ties) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   size_t x = row_begin + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -264,7 +257,7 @@ supercharge_kernel(const FT *__restrict__ queries, const FT *__restrict__ points
       if (out_dist) out_dist[orow * (size_t)k + p] = best.v[rr];
     }
   }
-  if (tie && tie_flags && lane == 0) tie_flags[orow] = 1;
+  if (tie && lane == 0) tie_report(ties, (u32)orow);
 }
 
 // ---- fast path (k <= 32, d in {16,32,64,128}) -------------------------------------------
@@ -292,8 +285,7 @@ supercharge_fast_kernel(const FT *__restrict__ queries, const FT *__restrict__ p
                         const u32 *__restrict__ own_ids, const FT *__restrict__ own_dist,
                         const u32 *__restrict__ graph, size_t n, int k, size_t row_begin,
                         size_t row_end, int exclude_self, int table_log2,
-                        u32 *__restrict__ out_ids, FT *__restrict__ out_dist,
-                        unsigned char *__restrict__ tie_flags) {
+                        u32 *__restrict__ out_ids, FT *__restrict__ out_dist, TieList ties) {
   constexpr int D = EPL * 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -407,68 +399,65 @@ supercharge_fast_kernel(const FT *__restrict__ queries, const FT *__restrict__ p
     out_ids[orow * (size_t)k + lane] = best.id[0];
     if (out_dist) out_dist[orow * (size_t)k + lane] = best.v[0];
   }
-  if (tie && lane == 0) tie_flags[orow] = 1;
+  if (tie && lane == 0) tie_report(ties, (u32)orow);
 }
 
-// Literal row of k(k+1) slots (supercharge + compdists + sort_and_uniq, alg.c:313-327).
+// Literal row of k(k+1) slots (supercharge + compdists + sort_and_uniq, alg.c:313-327), one
+// CTA per reported row (ties.rows == NULL: every row of the range).
 template <int E>
 __global__ void __launch_bounds__(256)
 supercharge_literal_kernel(const FT *__restrict__ queries, const FT *__restrict__ points,
                            const u32 *__restrict__ own_ids, const FT *__restrict__ own_dist,
                            const u32 *__restrict__ graph, size_t n, int d, int k, size_t row_begin,
                            size_t row_end, int exclude_self, u32 *__restrict__ out_ids,
-                           FT *__restrict__ out_dist, const unsigned char *__restrict__ tie_flags,
-                           unsigned char *scratch, size_t scratch_bytes, int *status) {
+                           FT *__restrict__ out_dist, TieList ties, unsigned char *slabs,
+                           size_t slab_bytes, int *status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int tid = threadIdx.x, wib = tid >> 5;
   FT *tmp = reinterpret_cast<FT *>(smem_raw) + (size_t)wib * (E == 0 ? d : 0);
-  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  const int wide = k * (k + 1);
-  const size_t slab = ((size_t)wide * (sizeof(u32) + sizeof(FT)) + 15) & ~(size_t)15;
-  const size_t slabs = scratch_bytes / slab;
-  if (slabs == 0) { if (warp == 0 && lane == 0) *status = 1; return; }
-  const size_t workers = slabs < nwarps ? slabs : nwarps;
-  if (warp >= workers) return;
-  FT *key = reinterpret_cast<FT *>(scratch + warp * slab);
-  u32 *ids = reinterpret_cast<u32 *>(key + wide);
-  const u32 sentinel = (u32)n;
   const size_t rows = row_end - row_begin;
+  const u32 total = ties.rows ? *ties.count : (u32)rows;
+  if (total == 0) return;
+  const int wide = k * (k + 1);
+  const size_t slab = ((size_t)wide * (2 * sizeof(u32) + sizeof(FT)) + 15) & ~(size_t)15;
+  const size_t fit = slab_bytes / slab;
+  if (fit == 0) { if (blockIdx.x == 0 && tid == 0) *status = 1; return; }
+  const u32 workers = (u32)(fit < gridDim.x ? fit : gridDim.x);
+  if (blockIdx.x >= workers) return;
+  if (blockIdx.x == 0 && tid == 0) atomicAdd(&finish_literal_rows_dev[1], (unsigned long long)total);
+  FT *key = reinterpret_cast<FT *>(slabs + (size_t)blockIdx.x * slab);
+  u32 *ids = reinterpret_cast<u32 *>(key + wide);
+  u32 *cslot = ids + wide;                                        // slots that need a distance
+  __shared__ u32 s_live;
+  const u32 sentinel = (u32)n;
 
-  for (size_t base = warp * 32; base < rows; base += workers * 32) {
-    size_t p = base + lane;
-    unsigned flagged = __ballot_sync(FULL, p < rows && (!tie_flags || tie_flags[p]));
-    while (flagged) {
-      int src = __ffs(flagged) - 1;
-      flagged &= flagged - 1;
-      const size_t orow = base + src, x = row_begin + orow;
-      if (lane == 0) atomicAdd(&finish_literal_rows_dev[1], 1ull);
-      for (int e = lane; e < k; e += 32) {
-        ids[e] = own_ids[x * (size_t)k + e];
-        key[e] = own_dist[x * (size_t)k + e];
-      }
-      __syncwarp();
-      for (int e = lane; e < k * k; e += 32) {                    // compute.cl:252-263
-        int j = e / k, z = e - j * k;
-        u32 oj = ids[j];
-        ids[k + e] = oj < sentinel ? graph[(size_t)oj * k + z] : sentinel;
-      }
-      __syncwarp();
-      for (int e = k; e < wide; e++) {
-        u32 cid = ids[e];
-        FT dist = ft_inf();
-        if (cid < sentinel && !(exclude_self && cid == (u32)x))
-          dist = row_sqdist<E>(queries + x * (size_t)d, points + (size_t)cid * d, d, tmp, lane);
-        if (lane == 0) key[e] = dist;
-      }
-      __syncwarp();
-      warp_sort_and_uniq(ids, key, wide, lane);
-      for (int i = lane; i < k; i += 32) {
-        out_ids[orow * (size_t)k + i] = ids[i];
-        if (out_dist) out_dist[orow * (size_t)k + i] = key[i];
-      }
-      __syncwarp();
+  for (u32 it = blockIdx.x; it < total; it += workers) {
+    const size_t orow = ties.rows ? ties.rows[it] : it, x = row_begin + orow;
+    if (tid == 0) s_live = 0;
+    for (int e = tid; e < k; e += blockDim.x) {
+      ids[e] = own_ids[x * (size_t)k + e];
+      key[e] = own_dist[x * (size_t)k + e];
     }
+    __syncthreads();
+    for (int e = tid; e < k * k; e += blockDim.x) {               // compute.cl:252-263
+      int j = e / k, z = e - j * k;
+      u32 oj = ids[j];
+      u32 cid = oj < sentinel ? graph[(size_t)oj * k + z] : sentinel;
+      ids[k + e] = cid;
+      key[k + e] = ft_inf();
+      if (cid < sentinel && !(exclude_self && cid == (u32)x)) cslot[atomicAdd(&s_live, 1u)] = (u32)(k + e);
+    }
+    __syncthreads();
+    block_row_distances<E>(queries + x * (size_t)d, points, d, s_live, tmp,
+                           [&](u32 i) { return (size_t)ids[cslot[i]]; },
+                           [&](u32 i, FT dist) { key[cslot[i]] = dist; });
+    __syncthreads();
+    block_sort_and_uniq(ids, key, wide);
+    for (int i = tid; i < k; i += blockDim.x) {
+      out_ids[orow * (size_t)k + i] = ids[i];
+      if (out_dist) out_dist[orow * (size_t)k + i] = key[i];
+    }
+    __syncthreads();
   }
 }
 
@@ -476,14 +465,14 @@ template <int E>
 static void launch_supercharge(int regs, size_t smem, annb_stream stream, const FT *queries,
                                const FT *points, const u32 *own_ids, const FT *own_dist,
                                const u32 *graph, size_t n, int d, int k, size_t rb, size_t re, int ex,
-                               u32 *out_ids, FT *out_dist, unsigned char *flags,
-                               unsigned char *slabs, size_t slab_bytes, int *status, bool all_literal, bool skip_main) {
+                               u32 *out_ids, FT *out_dist, const LiteralScratch &ls, int *status,
+                               bool all_literal, bool skip_main) {
   dim3 block(256), grid(grid_for((re - rb) * 32, 256));
 #define SC_CASE(R)                                                                               \
   {                                                                                              \
     if (smem > 48 * 1024)                                                                        \
       cudaFuncSetAttribute(supercharge_kernel<E, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    supercharge_kernel<E, R><<<grid, block, smem, stream>>>(queries, points, own_ids, own_dist, graph, n, d, k, rb, re, ex, out_ids, out_dist, flags); \
+    supercharge_kernel<E, R><<<grid, block, smem, stream>>>(queries, points, own_ids, own_dist, graph, n, d, k, rb, re, ex, out_ids, out_dist, ls.list); \
   }
   if (!all_literal && !skip_main) {
     switch (regs) {
@@ -497,9 +486,11 @@ static void launch_supercharge(int regs, size_t smem, annb_stream stream, const 
 #undef SC_CASE
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(supercharge_literal_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  supercharge_literal_kernel<E><<<all_literal ? 148 * 2 : 148, 256, smem, stream>>>(
-      queries, points, own_ids, own_dist, graph, n, d, k, rb, re, ex, out_ids, out_dist,
-      all_literal ? NULL : flags, slabs, slab_bytes, status);
+  TieList which = ls.list;
+  if (all_literal) which.rows = NULL;
+  supercharge_literal_kernel<E><<<all_literal ? 148 * 4 : 148 * 2, 256, smem, stream>>>(
+      queries, points, own_ids, own_dist, graph, n, d, k, rb, re, ex, out_ids, out_dist, which,
+      ls.slabs, ls.slab_bytes, status);
   LAUNCH_CHECK("supercharge_literal");
 }
 
@@ -515,12 +506,10 @@ extern "C" void annb_supercharge(const FT *queries, const FT *points, const u32 
   size_t smem = mode ? 0 : 8 * d * sizeof(FT);
   if (smem > 200 * 1024) fatal_config("d too large for the generic distance path");
   const size_t rows = row_end - row_begin;
-  unsigned char *flags = (unsigned char *)scratch;
-  unsigned char *slabs = (unsigned char *)(((uintptr_t)(flags + rows) + 255) & ~(uintptr_t)255);
-  size_t slab_bytes = scratch_bytes > rows + 512 ? scratch_bytes - rows - 512 : 0;
+  LiteralScratch ls = carve_literal_scratch(scratch, scratch_bytes, rows);
   const bool all_literal = k * (k + 1) < 16;      // the network degenerates: literal rows only
-  bool all_literal_redo_only = false;             // fast kernel already ran: only the flagged redo
-  if (!all_literal) cudaMemsetAsync(flags, 0, rows, stream);
+  bool all_literal_redo_only = false;             // fast kernel already ran: only the reported redo
+  cudaMemsetAsync(ls.list.count, 0, sizeof(u32), stream);
   // fast path
   {
     const char *off = getenv("ANN_B200_NO_FAST_SUPERCHARGE");
@@ -538,7 +527,7 @@ extern "C" void annb_supercharge(const FT *queries, const FT *points, const u32 
   {                                                                                                \
     if (fsmem > 48 * 1024)                                                                         \
       cudaFuncSetAttribute(supercharge_fast_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem); \
-    supercharge_fast_kernel<EE><<<grid, block, fsmem, stream>>>(queries, points, own_ids, own_dist, graph, n, (int)k, row_begin, row_end, exclude_self, tl, out_ids, out_dist, flags); \
+    supercharge_fast_kernel<EE><<<grid, block, fsmem, stream>>>(queries, points, own_ids, own_dist, graph, n, (int)k, row_begin, row_end, exclude_self, tl, out_ids, out_dist, ls.list); \
   }
       switch (epl) {
         case 2: FAST_CASE(2) break;
@@ -551,7 +540,7 @@ extern "C" void annb_supercharge(const FT *queries, const FT *points, const u32 
       all_literal_redo_only = true;
     }
   }
-#define SC_ARGS regs, smem, stream, queries, points, own_ids, own_dist, graph, n, (int)d, (int)k, row_begin, row_end, exclude_self, out_ids, out_dist, flags, slabs, slab_bytes, status, all_literal, all_literal_redo_only
+#define SC_ARGS regs, smem, stream, queries, points, own_ids, own_dist, graph, n, (int)d, (int)k, row_begin, row_end, exclude_self, out_ids, out_dist, ls, status, all_literal, all_literal_redo_only
   switch (mode) {
     case 0: launch_supercharge<0>(SC_ARGS); break;
     case 1: launch_supercharge<1>(SC_ARGS); break;

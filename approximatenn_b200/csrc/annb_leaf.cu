@@ -30,8 +30,7 @@ __global__ void __launch_bounds__(256)
 leaf_topk_warp_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
                       const u32 *__restrict__ offset, const u32 *__restrict__ hash,
                       const u32 *__restrict__ tmax_p, size_t n, int d, int d_short, int k,
-                      u32 *__restrict__ list_ids, FT *__restrict__ list_dist,
-                      unsigned char *__restrict__ tie_flags) {
+                      u32 *__restrict__ list_ids, FT *__restrict__ list_dist, TieList ties) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   size_t r = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // sorted position
@@ -81,7 +80,7 @@ leaf_topk_warp_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
       list_dist[(size_t)me * k + p] = best.v[rr];
     }
   }
-  if (tie && lane == 0) tie_flags[me] = 1;
+  if (tie && lane == 0) tie_report(ties, me);
 }
 
 // =====================================================================================
@@ -203,8 +202,7 @@ __global__ void __launch_bounds__(TILE_WARPS * 32)
 leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
                       const u32 *__restrict__ offset, const u32 *__restrict__ tmax_p, size_t n,
                       size_t buckets, int d_short, int k, u32 *__restrict__ list_ids,
-                      FT *__restrict__ list_dist, unsigned char *__restrict__ tie_flags,
-                      int pack_tries, int max_slices) {
+                      FT *__restrict__ list_dist, TieList ties, int pack_tries, int max_slices) {
   typedef TileSmem<D, KC> SM;
   constexpr int RS = SM::RS;
   constexpr int PPR = D / VW;                                          // 16-byte pieces per row
@@ -378,20 +376,19 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
           list_dist[(size_t)my_id * k + i] = ld[i];
           if (i + 1 < KC && ld[i] == ld[i + 1] && ld[i] != ft_inf()) tie = true;
         }
-      if (tie) tie_flags[my_id] = 1;
+      if (tie) tie_report(ties, my_id);
     }
     __syncwarp();
   }
 }
 
 // =====================================================================================
-// literal rows for flagged points (exact ties)
+// literal rows for reported points (exact ties)
 // =====================================================================================
-// Builds the reference's candidate row of one point (all (d_short+1)*tmax slots, pads and
-// self at +inf), runs its sorting network / duplicate rule / sorting network, and rewrites
-// the point's list.  Row storage is a slab of `slab_slots` (id, key) slots per warp in
-// global scratch; warps without a slab (scratch too small for them) do nothing, and if not
-// even one fits, *status is set.
+// One CTA per reported point: builds the reference's candidate row (all (d_short+1)*tmax
+// slots, pads and self at +inf), runs its sorting network / duplicate rule / sorting
+// network, and rewrites the point's list.  Row storage is one slab per CTA in global
+// scratch; CTAs without a slab do nothing, and if not even one fits, *status is set.
 
 template <int E>
 __global__ void __launch_bounds__(256)
@@ -399,74 +396,64 @@ leaf_literal_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
                     const u32 *__restrict__ offset, const u32 *__restrict__ hash,
                     const u32 *__restrict__ rank_of, const u32 *__restrict__ tmax_p, size_t n, int d,
                     int d_short, int k, u32 *__restrict__ list_ids, FT *__restrict__ list_dist,
-                    const unsigned char *__restrict__ tie_flags, unsigned char *scratch,
-                    size_t scratch_bytes, int *status) {
+                    TieList ties, unsigned char *slabs, size_t slab_bytes, int *status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  __shared__ u32 s_beg[33], s_cnt[33], s_pos[34];
+  const int tid = threadIdx.x, wib = tid >> 5;
   FT *tmp = reinterpret_cast<FT *>(smem_raw) + (size_t)wib * (E == 0 ? d : 0);
-  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const u32 total = *ties.count;
+  if (total == 0) return;
   const unsigned long long tmax = *tmax_p;
   const size_t L = (size_t)(d_short + 1) * tmax;
-  const size_t slab = (L * (sizeof(u32) + sizeof(FT)) + 15) & ~(size_t)15;
-  const size_t slabs = slab ? scratch_bytes / slab : 0;
-  if (slabs == 0) { if (warp == 0 && lane == 0) *status = 1; return; }
-  const size_t workers = slabs < nwarps ? slabs : nwarps;
-  if (warp >= workers) return;
-  FT *key = reinterpret_cast<FT *>(scratch + warp * slab);
+  const size_t slab = (L * (sizeof(FT) + 3 * sizeof(u32)) + 15) & ~(size_t)15;
+  const size_t fit = slab ? slab_bytes / slab : 0;
+  if (fit == 0) { if (blockIdx.x == 0 && tid == 0) *status = 1; return; }
+  const u32 workers = (u32)(fit < gridDim.x ? fit : gridDim.x);
+  if (blockIdx.x >= workers) return;
+  if (blockIdx.x == 0 && tid == 0) atomicAdd(&leaf_literal_rows_dev, (unsigned long long)total);
+  FT *key = reinterpret_cast<FT *>(slabs + (size_t)blockIdx.x * slab);
   u32 *ids = reinterpret_cast<u32 *>(key + L);
+  u32 *crow = ids + L, *cslot = crow + L;
   const u32 sentinel = (u32)n;
 
-  for (size_t base = warp * 32; base < n; base += workers * 32) {
-    size_t p = base + lane;
-    unsigned flagged = __ballot_sync(FULL, p < n && tie_flags[p]);
-    while (flagged) {
-      int src = __ffs(flagged) - 1;
-      flagged &= flagged - 1;
-      const u32 x = (u32)(base + src);
-      if (lane == 0) atomicAdd(&leaf_literal_rows_dev, 1ull);
-      const u32 h = hash[x];
-      const size_t xr = rank_of[x];                               // sorted position of x
-      for (int y = 0; y <= d_short; y++) {
-        u32 b = h ^ (y ? (1u << (y - 1)) : 0u);
-        u32 beg = offset[b], cnt = offset[b + 1] - beg;
-        for (u32 z = lane; z < (u32)tmax; z += 32) ids[(size_t)y * tmax + z] = z < cnt ? order[beg + z] : sentinel;
-        if (E) {
-          WarpRow<(E ? E : 1)> qr;
-          qr.load(sp + xr * (size_t)d, lane, d);
-          for (u32 z0 = 0; z0 < cnt; z0 += 8) {                     // 8 candidate rows in flight
-            WarpRow<(E ? E : 1)> cr[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-              size_t row = (size_t)beg + min(z0 + u, cnt - 1);
-              cr[u].load(sp + row * (size_t)d, lane, d);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-              FT dist = __shfl_sync(FULL, warp_sqdist<(E ? E : 1)>(qr, cr[u], d), 0);
-              u32 z = z0 + u;
-              if ((size_t)beg + z == xr) dist = ft_inf();
-              if (lane == 0 && z < cnt) key[(size_t)y * tmax + z] = dist;
-            }
-          }
-          for (u32 z = cnt + lane; z < (u32)tmax; z += 32) key[(size_t)y * tmax + z] = ft_inf();
-        } else {
-          for (u32 z = 0; z < (u32)tmax; z++) {
-            FT dist = ft_inf();
-            if (z < cnt && (size_t)beg + z != xr)
-              dist = generic_sqdist(sp + xr * (size_t)d, sp + ((size_t)beg + z) * d, d, tmp, lane);
-            if (lane == 0) key[(size_t)y * tmax + z] = dist;
-          }
-        }
-      }
-      __syncwarp();
-      warp_sort_and_uniq(ids, key, (int)L, lane);
-      for (int i = lane; i < k; i += 32) {
-        list_ids[(size_t)x * k + i] = ids[i];
-        list_dist[(size_t)x * k + i] = key[i];
-      }
-      __syncwarp();
+  for (u32 it = blockIdx.x; it < total; it += workers) {
+    const u32 x = ties.rows[it];
+    const u32 h = hash[x];
+    const u32 xr = rank_of[x];                                    // sorted position of x
+    if (tid <= d_short) {
+      u32 b = h ^ (tid ? (1u << (tid - 1)) : 0u);
+      s_beg[tid] = offset[b];
+      s_cnt[tid] = offset[b + 1] - offset[b];
     }
+    __syncthreads();
+    if (tid == 0) {
+      u32 pos = 0;
+      for (int y = 0; y <= d_short; y++) { s_pos[y] = pos; pos += s_cnt[y]; }
+      s_pos[d_short + 1] = pos;
+    }
+    __syncthreads();
+    for (size_t slot = tid; slot < L; slot += blockDim.x) {
+      u32 y = (u32)(slot / tmax), z = (u32)(slot - (size_t)y * tmax);
+      bool real = z < s_cnt[y];
+      ids[slot] = real ? order[s_beg[y] + z] : sentinel;
+      key[slot] = ft_inf();                                       // pads, and self below
+      if (real) {
+        u32 f = s_pos[y] + z;
+        crow[f] = s_beg[y] + z;
+        cslot[f] = (u32)slot;
+      }
+    }
+    __syncthreads();
+    block_row_distances<E>(sp + (size_t)xr * d, sp, d, s_pos[d_short + 1], tmp,
+                           [&](u32 i) { return (size_t)crow[i]; },
+                           [&](u32 i, FT dist) { if (crow[i] != xr) key[cslot[i]] = dist; });
+    __syncthreads();
+    block_sort_and_uniq(ids, key, (int)L);
+    for (int i = tid; i < k; i += blockDim.x) {
+      list_ids[(size_t)x * k + i] = ids[i];
+      list_dist[(size_t)x * k + i] = key[i];
+    }
+    __syncthreads();
   }
 }
 
@@ -484,7 +471,7 @@ template <int E>
 static void launch_warp_r(int regs, dim3 grid, dim3 block, size_t smem, annb_stream stream,
                           const FT *sp, const u32 *order, const u32 *offset, const u32 *hash,
                           const u32 *tmax, size_t n, int d, int d_short, int k, u32 *ids, FT *dist,
-                          unsigned char *flags) {
+                          TieList flags) {
 #define WARP_CASE(R)                                                                             \
   {                                                                                              \
     if (smem > 48 * 1024)                                                                        \
@@ -503,7 +490,7 @@ static void launch_warp_r(int regs, dim3 grid, dim3 block, size_t smem, annb_str
 template <int D, int KC>
 static void launch_tile(annb_stream stream, const FT *sp, const u32 *order, const u32 *offset,
                         const u32 *tmax, size_t n, size_t buckets, int d_short, int k, u32 *ids,
-                        FT *dist, unsigned char *flags) {
+                        FT *dist, TieList flags) {
   size_t smem = TileSmem<D, KC>::per_warp * TILE_WARPS;
   static bool configured = false;
   if (!configured) {
@@ -526,7 +513,7 @@ static void launch_tile(annb_stream stream, const FT *sp, const u32 *order, cons
 // returns false when no tiled instantiation covers (d, k)
 static bool try_launch_tile(annb_stream stream, const FT *sp, const u32 *order, const u32 *offset,
                             const u32 *tmax, size_t n, size_t buckets, size_t d, int d_short,
-                            size_t k, u32 *ids, FT *dist, unsigned char *flags) {
+                            size_t k, u32 *ids, FT *dist, TieList flags) {
   const char *off = getenv("ANN_B200_NO_TILE");
   if (off && *off && *off != '0') return false;
   if (d_short > 31) return false;
@@ -548,7 +535,7 @@ static bool try_launch_tile(annb_stream stream, const FT *sp, const u32 *order, 
   return false;
 }
 
-extern "C" size_t annb_leaf_scratch_bytes(size_t n) { return n * sizeof(u32) + n + (64u << 20) + 256; }
+extern "C" size_t annb_leaf_scratch_bytes(size_t n) { return 2 * n * sizeof(u32) + (64u << 20) + 1024; }
 
 extern "C" void annb_leaf_topk(const FT *sorted_points, const u32 *order, const u32 *offset,
                                const u32 *hash, const u32 *tmax, size_t n, size_t d,
@@ -556,12 +543,14 @@ extern "C" void annb_leaf_topk(const FT *sorted_points, const u32 *order, const 
                                void *scratch, int *status, annb_stream stream) {
   int regs = list_regs(k);
   if (!regs) fatal_config("k > 256");
-  // scratch layout: rank_of[n] | flags[n] | literal-row slabs
+  // scratch layout: rank_of[n] | tie list (count, rows[n]) | literal-row slabs
   u32 *rank_of = (u32 *)scratch;
-  unsigned char *flags = (unsigned char *)(rank_of + n);
-  unsigned char *slabs = (unsigned char *)(((uintptr_t)(flags + n) + 255) & ~(uintptr_t)255);
-  size_t slab_bytes = 64u << 20;
-  cudaMemsetAsync(flags, 0, n, stream);
+  const size_t rank_bytes = (n * sizeof(u32) + 255) & ~(size_t)255;
+  LiteralScratch ls = carve_literal_scratch((unsigned char *)scratch + rank_bytes, annb_leaf_scratch_bytes(n) - rank_bytes, n);
+  TieList flags = ls.list;
+  unsigned char *slabs = ls.slabs;
+  size_t slab_bytes = ls.slab_bytes;
+  cudaMemsetAsync(flags.count, 0, sizeof(u32), stream);
   const size_t buckets = (size_t)1 << d_short;
   int mode = row_mode(d);
   size_t gsmem = mode ? 0 : 8 * d * sizeof(FT);
@@ -584,7 +573,7 @@ extern "C" void annb_leaf_topk(const FT *sorted_points, const u32 *order, const 
 
   invert_order_kernel<<<grid_for(n, 256), 256, 0, stream>>>(order, n, rank_of);
   LAUNCH_CHECK("invert_order");
-  dim3 lblock(256), lgrid(148);
+  dim3 lblock(256), lgrid(148 * 4);
 #define L_ARGS sorted_points, order, offset, hash, rank_of, tmax, n, (int)d, (int)d_short, (int)k, list_ids, list_dist, flags, slabs, slab_bytes, status
 #define L_CASE(EE)                                                                                \
   {                                                                                               \

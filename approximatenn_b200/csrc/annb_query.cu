@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256)
 query_rows_kernel(const FT *__restrict__ y, const FT *__restrict__ points, QueryTables q,
                   const u32 *__restrict__ sign, size_t n, size_t ycnt, int d, int d_short, int k,
                   int exclude_self, u32 *__restrict__ list_ids, FT *__restrict__ list_dist,
-                  unsigned char *__restrict__ tie_flags) {
+                  TieList ties) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   size_t x = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -143,78 +143,76 @@ query_rows_kernel(const FT *__restrict__ y, const FT *__restrict__ points, Query
       list_dist[x * (size_t)k + p] = best.v[rr];
     }
   }
-  if (tie && lane == 0) tie_flags[x] = 1;
+  if (tie && lane == 0) tie_report(ties, (u32)x);
 }
 
-// literal row of a flagged query: every column, the reference's network, first k out
+// literal row of a reported query: every column, the reference's network, first k out;
+// one CTA per row
 template <int E>
 __global__ void __launch_bounds__(256)
 query_literal_kernel(const FT *__restrict__ y, const FT *__restrict__ points, QueryTables q,
                      const u32 *__restrict__ sign, size_t n, size_t ycnt, int d, int d_short, int k,
                      int exclude_self, u32 *__restrict__ list_ids, FT *__restrict__ list_dist,
-                     const unsigned char *__restrict__ tie_flags, unsigned char *scratch,
-                     size_t scratch_bytes, int *status) {
+                     TieList ties, unsigned char *slabs, size_t slab_bytes, int *status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int tid = threadIdx.x, wib = tid >> 5;
   FT *tmp = reinterpret_cast<FT *>(smem_raw) + (size_t)wib * (E == 0 ? d : 0);
-  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const u32 total = *ties.count;
+  if (total == 0) return;
   const size_t L = (size_t)q.len;
-  const size_t slab = (L * (sizeof(u32) + sizeof(FT)) + 15) & ~(size_t)15;
-  const size_t slabs = slab ? scratch_bytes / slab : 0;
-  if (slabs == 0) { if (warp == 0 && lane == 0) *status = 1; return; }
-  const size_t workers = slabs < nwarps ? slabs : nwarps;
-  if (warp >= workers) return;
-  FT *key = reinterpret_cast<FT *>(scratch + warp * slab);
+  const size_t slab = (L * (sizeof(FT) + 2 * sizeof(u32)) + 15) & ~(size_t)15;
+  const size_t fit = slab ? slab_bytes / slab : 0;
+  if (fit == 0) { if (blockIdx.x == 0 && tid == 0) *status = 1; return; }
+  const u32 workers = (u32)(fit < gridDim.x ? fit : gridDim.x);
+  if (blockIdx.x >= workers) return;
+  if (blockIdx.x == 0 && tid == 0) atomicAdd(&query_literal_rows_dev, (unsigned long long)total);
+  FT *key = reinterpret_cast<FT *>(slabs + (size_t)blockIdx.x * slab);
   u32 *ids = reinterpret_cast<u32 *>(key + L);
+  u32 *cslot = ids + L;
+  __shared__ u32 s_live;
   const u32 sentinel = (u32)n;
 
-  for (size_t base = warp * 32; base < ycnt; base += workers * 32) {
-    size_t p = base + lane;
-    unsigned flagged = __ballot_sync(FULL, p < ycnt && (!tie_flags || tie_flags[p]));
-    while (flagged) {
-      int src = __ffs(flagged) - 1;
-      flagged &= flagged - 1;
-      const size_t x = base + src;
-      if (lane == 0) atomicAdd(&query_literal_rows_dev, 1ull);
-      for (int t = 0; t < q.tries; t++) {
-        const u32 h = sign[(size_t)t * ycnt + x];
-        const u32 w = q.width[t];
-        for (int f = 0; f <= d_short; f++) {
-          size_t col = (size_t)(d_short + 1) * q.offset[t] + (size_t)f * w;
-          const u32 *row = q.tab[t] + (size_t)(h ^ (f ? (1u << (f - 1)) : 0u)) * w;
-          for (u32 z = lane; z < w; z += 32) ids[col + z] = row[z];
-          for (u32 z = 0; z < w; z++) {
-            u32 id = row[z];
-            FT dist = ft_inf();
-            if (id < sentinel && !(exclude_self && id == (u32)x))
-              dist = row_sqdist<E>(y + x * (size_t)d, points + (size_t)id * d, d, tmp, lane);
-            if (lane == 0) key[col + z] = dist;
-          }
-        }
+  for (u32 it = blockIdx.x; it < total; it += workers) {
+    const size_t x = ties.rows[it];
+    if (tid == 0) s_live = 0;
+    __syncthreads();
+    for (int t = 0; t < q.tries; t++) {
+      const u32 h = sign[(size_t)t * ycnt + x];
+      const u32 w = q.width[t];
+      const size_t cols = (size_t)(d_short + 1) * w, col0 = (size_t)(d_short + 1) * q.offset[t];
+      for (size_t c = tid; c < cols; c += blockDim.x) {
+        u32 f = (u32)(c / w), z = (u32)(c - (size_t)f * w);
+        u32 id = q.tab[t][(size_t)(h ^ (f ? (1u << (f - 1)) : 0u)) * w + z];
+        ids[col0 + c] = id;
+        key[col0 + c] = ft_inf();
+        if (id < sentinel && !(exclude_self && id == (u32)x)) cslot[atomicAdd(&s_live, 1u)] = (u32)(col0 + c);
       }
-      __syncwarp();
-      warp_sort_and_uniq(ids, key, (int)L, lane);
-      for (int i = lane; i < k; i += 32) {
-        list_ids[x * (size_t)k + i] = ids[i];
-        list_dist[x * (size_t)k + i] = key[i];
-      }
-      __syncwarp();
     }
+    __syncthreads();
+    block_row_distances<E>(y + x * (size_t)d, points, d, s_live, tmp,
+                           [&](u32 i) { return (size_t)ids[cslot[i]]; },
+                           [&](u32 i, FT dist) { key[cslot[i]] = dist; });
+    __syncthreads();
+    block_sort_and_uniq(ids, key, (int)L);
+    for (int i = tid; i < k; i += blockDim.x) {
+      list_ids[x * (size_t)k + i] = ids[i];
+      list_dist[x * (size_t)k + i] = key[i];
+    }
+    __syncthreads();
   }
 }
 
 template <int E>
 static void launch_query_rows(int regs, size_t smem, annb_stream stream, const FT *y, const FT *points,
                               const QueryTables &q, const u32 *sign, size_t n, size_t ycnt, int d,
-                              int d_short, int k, int ex, u32 *ids, FT *dist, unsigned char *flags,
-                              unsigned char *slabs, size_t slab_bytes, int *status) {
+                              int d_short, int k, int ex, u32 *ids, FT *dist, const LiteralScratch &ls,
+                              int *status) {
   dim3 block(256), grid(grid_for(ycnt * 32, 256));
 #define QR_CASE(R)                                                                                \
   {                                                                                               \
     if (smem > 48 * 1024)                                                                         \
       cudaFuncSetAttribute(query_rows_kernel<E, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    query_rows_kernel<E, R><<<grid, block, smem, stream>>>(y, points, q, sign, n, ycnt, d, d_short, k, ex, ids, dist, flags); \
+    query_rows_kernel<E, R><<<grid, block, smem, stream>>>(y, points, q, sign, n, ycnt, d, d_short, k, ex, ids, dist, ls.list); \
   }
   switch (regs) {
     case 1: QR_CASE(1) break;
@@ -226,7 +224,7 @@ static void launch_query_rows(int regs, size_t smem, annb_stream stream, const F
   LAUNCH_CHECK("query_rows");
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(query_literal_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  query_literal_kernel<E><<<148, 256, smem, stream>>>(y, points, q, sign, n, ycnt, d, d_short, k, ex, ids, dist, flags, slabs, slab_bytes, status);
+  query_literal_kernel<E><<<148 * 2, 256, smem, stream>>>(y, points, q, sign, n, ycnt, d, d_short, k, ex, ids, dist, ls.list, ls.slabs, ls.slab_bytes, status);
   LAUNCH_CHECK("query_literal");
 }
 
@@ -253,11 +251,9 @@ extern "C" void annb_query_rows(const FT *y, const FT *points, const u32 *const 
   int mode = row_mode(d);
   size_t smem = mode ? 0 : 8 * d * sizeof(FT);
   if (smem > 200 * 1024) fatal_config("d too large for the generic distance path");
-  unsigned char *flags = (unsigned char *)scratch;
-  unsigned char *slabs = (unsigned char *)(((uintptr_t)(flags + ycnt) + 255) & ~(uintptr_t)255);
-  size_t slab_bytes = scratch_bytes > ycnt + 512 ? scratch_bytes - ycnt - 512 : 0;
-  cudaMemsetAsync(flags, 0, ycnt, stream);
-#define Q_ARGS regs, smem, stream, y, points, q, sign, n, ycnt, (int)d, (int)d_short, (int)k, exclude_self, list_ids, list_dist, flags, slabs, slab_bytes, status
+  LiteralScratch ls = carve_literal_scratch(scratch, scratch_bytes, ycnt);
+  cudaMemsetAsync(ls.list.count, 0, sizeof(u32), stream);
+#define Q_ARGS regs, smem, stream, y, points, q, sign, n, ycnt, (int)d, (int)d_short, (int)k, exclude_self, list_ids, list_dist, ls, status
   switch (mode) {
     case 0: launch_query_rows<0>(Q_ARGS); break;
     case 1: launch_query_rows<1>(Q_ARGS); break;

@@ -64,36 +64,58 @@ def synth_points(n, d, dtype, seed=1):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks/throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons while the timed region runs.  NVML in-process (a
+    `nvidia-smi` subprocess every 100 ms costs the timed region ~10 ms per step); falls back to
+    one nvidia-smi query per second if NVML is unavailable."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.idx, self.stop_flag, self.rows = gpu_index, threading.Event(), []
+        self.idx, self.stop_flag = gpu_index, threading.Event()
+        self.sm, self.mx, self.reasons, self.how = [], [], set(), "nvml"
+
+    def _nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+        self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)))
+        while not self.stop_flag.is_set():
+            self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for name, bit in self.REASONS:
+                if mask & bit:
+                    self.reasons.add(name)
+            self.stop_flag.wait(0.02)
+
+    def _smi(self):
+        self.how = "nvidia-smi"
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                 timeout=10).stdout.strip().split(",")
+            if len(out) >= 6:
+                self.sm.append(float(out[0])); self.mx.append(float(out[1]))
+                for (name, _), v in zip(self.REASONS, out[2:6]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(name)
+            self.stop_flag.wait(1.0)
 
     def run(self):
-        while not self.stop_flag.is_set():
+        try:
+            self._nvml()
+        except Exception:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self._smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4)
-                          if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None,
+                "sm_max_mhz": max(self.mx) if self.mx else None, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": self.how}
 
 
 def cpu_baseline(cfg, pts, sample_points):
@@ -167,6 +189,12 @@ def main():
         run_reference_arm(args, cfg, args.config)
         return
 
+    # keep stdout clean for the one JSON line: native libraries (NCCL's version banner) write
+    # to fd 1 directly, so fd 1 points at stderr until the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -233,6 +261,10 @@ def main():
         t = torch.tensor([dev_total_s, wall], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_total_s, wall = float(t[0]), float(t[1])
+    if world > 1:
+        gpu.lib.annb200_dist_shutdown()
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
 
@@ -262,6 +294,8 @@ def main():
             "clocks": sampler.summary()}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, pts, args.cpu_sample)
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
 
 
