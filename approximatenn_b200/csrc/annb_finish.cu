@@ -261,30 +261,19 @@ supercharge_kernel(const FT *__restrict__ queries, const FT *__restrict__ points
 }
 
 // ---- fast path (k <= 32, d in {16,32,64,128}) -------------------------------------------
-// Neighbour-of-neighbour lists repeat the same ids many times, and equal ids have equal
-// distances, so the candidate ids of a row are de-duplicated FIRST (a per-warp hash set in
-// shared memory, seeded with the own list) and only the distinct ones are gathered.  Four
-// candidates are measured per step: 8 lanes per candidate, lane g holding coordinates
-// g, g+8, g+16, ... so that the first levels of the reference's summation tree are
-// lane-local and the last three are xor-shuffles inside the 8-lane group.
-#define HS_EMPTY 0xffffffffu
-
-__device__ __forceinline__ bool hs_insert(u32 *tab, u32 mask, int shift, u32 id) {
-  u32 h = (id * 2654435761u) >> shift;
-  while (true) {
-    u32 old = atomicCAS(&tab[h], HS_EMPTY, id);
-    if (old == HS_EMPTY) return true;
-    if (old == id) return false;
-    h = (h + 1) & mask;
-  }
-}
-
+// One warp per row.  The candidate ids of the row (the neighbours' lists) are staged in
+// shared memory with coalesced loads; candidates are then measured eight at a time, 8 lanes
+// per candidate: lane g holds coordinates g, g+8, g+16, ... so that the first levels of the
+// reference's summation tree are lane-local and the last three are xor-shuffles inside the
+// 8-lane group.  After 8 tries hardly any candidate beats the current k-th best (3 % at
+// cfg3), so the per-lane list is only touched when a ballot says some candidate passes;
+// repeated ids are caught there (equal ids have equal distances).
 template <int EPL>
 __global__ void __launch_bounds__(256)
 supercharge_fast_kernel(const FT *__restrict__ queries, const FT *__restrict__ points,
                         const u32 *__restrict__ own_ids, const FT *__restrict__ own_dist,
                         const u32 *__restrict__ graph, size_t n, int k, size_t row_begin,
-                        size_t row_end, int exclude_self, int table_log2,
+                        size_t row_end, int exclude_self,
                         u32 *__restrict__ out_ids, FT *__restrict__ out_dist, TieList ties) {
   constexpr int D = EPL * 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -295,12 +284,7 @@ supercharge_fast_kernel(const FT *__restrict__ queries, const FT *__restrict__ p
   const int wide = k * (k + 1);
   const int P2 = 1 << floor_log2_u((unsigned long long)wide);
   const int cand = P2 - k;
-  const u32 tsize = 1u << table_log2, tmask = tsize - 1;
-  const int shift = 32 - table_log2;
-  u32 *tab = reinterpret_cast<u32 *>(smem_raw) + (size_t)wib * (tsize + (size_t)k * k);
-  u32 *uniq = tab + tsize;
-
-  for (u32 i = lane; i < tsize; i += 32) tab[i] = HS_EMPTY;
+  u32 *uniq = reinterpret_cast<u32 *>(smem_raw) + (size_t)wib * ((size_t)k * k);
 
   const int g = lane & 7, grp = lane >> 3;
   FT q[EPL];
@@ -329,13 +313,7 @@ supercharge_fast_kernel(const FT *__restrict__ queries, const FT *__restrict__ p
     if (ov > max_v) { max_v = ov; max_id = oi; }
   }
   FT tau = best.kth(k);
-  __syncwarp();
-  // only FINITE own entries stand for their id (an id carried with +inf may come back finite)
-  if (lane < k && own_reg < sentinel && best.v[0] != ft_inf()) hs_insert(tab, tmask, shift, own_reg);
-  if (exclude_self && lane == 0) hs_insert(tab, tmask, shift, (u32)x);
-  __syncwarp();
-
-  // distinct candidate ids -> uniq[0..U)
+  // candidate ids -> uniq[0..U): pads and (in precomp) the point itself are dropped here
   int U = 0;
   for (int base = 0; base < cand; base += 32) {
     int c = base + lane;
@@ -346,7 +324,7 @@ supercharge_fast_kernel(const FT *__restrict__ queries, const FT *__restrict__ p
     bool keep = false;
     if (c < cand) {
       if (cid >= sentinel || (exclude_self && cid == (u32)x)) any_inf = true;
-      else keep = hs_insert(tab, tmask, shift, cid);
+      else keep = true;
     }
     unsigned m = __ballot_sync(FULL, keep);
     if (keep) uniq[U + __popc(m & ((1u << lane) - 1))] = cid;
@@ -356,38 +334,67 @@ supercharge_fast_kernel(const FT *__restrict__ queries, const FT *__restrict__ p
   tie = __any_sync(FULL, tie);
   __syncwarp();
 
-  for (int base = 0; base < U; base += 4) {
-    int mine = base + grp;
-    u32 cid = uniq[mine < U ? mine : base];
-    const FT *crow = points + (size_t)cid * D;
-    FT m[EPL];
+  // Eight candidates per iteration (two groups of four in flight).  After 8 tries almost no
+  // candidate beats the k-th best, so the lists are only touched when some lane's candidate
+  // passes a ballot; the running (max, id) for the prefix-corner rule stays lane-local.
+  FT lmax_v = -ft_inf();
+  u32 lmax_id = sentinel;
+  for (int base = 0; base < U; base += 8) {
+    u32 cid[2];
+    FT v[2];
+    FT m[2][EPL];
 #pragma unroll
-    for (int s = 0; s < EPL; s++) {
-      FT df = q[s] - crow[g + 8 * s];
-      m[s] = df * df;
+    for (int h2 = 0; h2 < 2; h2++) {
+      int mine = base + 4 * h2 + grp;
+      cid[h2] = uniq[mine < U ? mine : base];
+      const FT *crow = points + (size_t)cid[h2] * D;
+#pragma unroll
+      for (int s = 0; s < EPL; s++) m[h2][s] = crow[g + 8 * s];
     }
 #pragma unroll
-    for (int h = EPL / 2; h >= 1; h >>= 1)
+    for (int h2 = 0; h2 < 2; h2++) {
 #pragma unroll
-      for (int s = 0; s < h; s++) m[s] = m[s] + m[s + h];
-    FT v = m[0];
-    v = v + __shfl_xor_sync(FULL, v, 4);
-    v = v + __shfl_xor_sync(FULL, v, 2);
-    v = v + __shfl_xor_sync(FULL, v, 1);
-    int cnt = min(4, U - base);
-    for (int i = 0; i < cnt; i++) {
-      FT vn = __shfl_sync(FULL, v, 8 * i);
-      u32 idn = __shfl_sync(FULL, cid, 8 * i);
-      if (vn > max_v) { max_v = vn; max_id = idn; }
-      if (vn < tau) {
-        if (__any_sync(FULL, best.v[0] == vn)) tie = true;
-        best.insert(vn, idn, k, sentinel, lane);
-        tau = best.kth(k);
-      } else if (vn == tau && vn != ft_inf()) {
-        tie = true;
+      for (int s = 0; s < EPL; s++) {
+        FT df = q[s] - m[h2][s];
+        m[h2][s] = df * df;
       }
+#pragma unroll
+      for (int h = EPL / 2; h >= 1; h >>= 1)
+#pragma unroll
+        for (int s = 0; s < h; s++) m[h2][s] = m[h2][s] + m[h2][s + h];
+      FT t = m[h2][0];
+      t = t + __shfl_xor_sync(FULL, t, 4);
+      t = t + __shfl_xor_sync(FULL, t, 2);
+      t = t + __shfl_xor_sync(FULL, t, 1);
+      bool live = base + 4 * h2 + grp < U;
+      v[h2] = live ? t : ft_inf();
+      if (live && t > lmax_v) { lmax_v = t; lmax_id = cid[h2]; }
+    }
+    if (__any_sync(FULL, v[0] <= tau || v[1] <= tau)) {
+#pragma unroll
+      for (int h2 = 0; h2 < 2; h2++)
+        for (int i = 0; i < 4; i++) {
+          FT vn = __shfl_sync(FULL, v[h2], 8 * i);
+          u32 idn = __shfl_sync(FULL, cid[h2], 8 * i);
+          if (vn <= tau && vn != ft_inf() && !best.contains(idn)) {
+            if (vn < tau) {
+              if (__any_sync(FULL, best.v[0] == vn)) tie = true;
+              best.insert(vn, idn, k, sentinel, lane);
+              tau = best.kth(k);
+            } else {
+              tie = true;
+            }
+          }
+        }
     }
   }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    FT ov = __shfl_xor_sync(FULL, lmax_v, o);
+    u32 oi = __shfl_xor_sync(FULL, lmax_id, o);
+    if (ov > lmax_v) { lmax_v = ov; lmax_id = oi; }
+  }
+  if (lmax_v > max_v) { max_v = lmax_v; max_id = lmax_id; }
   if (P2 < wide && !any_inf) {
     int c = P2 - k, j = c / k, z = c - j * k;
     u32 oj = __shfl_sync(FULL, own_reg, j);
@@ -516,18 +523,13 @@ extern "C" void annb_supercharge(const FT *queries, const FT *points, const u32 
     bool allow = !(off && *off && *off != '0');
     int epl = (d == 16 || d == 32 || d == 64 || d == 128) ? (int)(d / 8) : 0;
     if (allow && !all_literal && k <= 32 && epl) {
-      int P2 = 1;
-      while ((size_t)P2 * 2 <= k * (k + 1)) P2 *= 2;
-      int tl = 5;
-      while ((1u << tl) < 2u * (unsigned)P2) tl++;
-      size_t per_warp = ((size_t)(1u << tl) + k * k) * sizeof(u32);
-      size_t fsmem = per_warp * 8;
+      size_t fsmem = k * k * sizeof(u32) * 8;
       dim3 block(256), grid(grid_for(rows * 32, 256));
 #define FAST_CASE(EE)                                                                              \
   {                                                                                                \
     if (fsmem > 48 * 1024)                                                                         \
       cudaFuncSetAttribute(supercharge_fast_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem); \
-    supercharge_fast_kernel<EE><<<grid, block, fsmem, stream>>>(queries, points, own_ids, own_dist, graph, n, (int)k, row_begin, row_end, exclude_self, tl, out_ids, out_dist, ls.list); \
+    supercharge_fast_kernel<EE><<<grid, block, fsmem, stream>>>(queries, points, own_ids, own_dist, graph, n, (int)k, row_begin, row_end, exclude_self, out_ids, out_dist, ls.list); \
   }
       switch (epl) {
         case 2: FAST_CASE(2) break;
