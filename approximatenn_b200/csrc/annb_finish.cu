@@ -40,6 +40,8 @@ merge_lists_kernel(const u32 *__restrict__ lists_ids, const FT *__restrict__ lis
   u32 max_id = sentinel;
   bool any_inf = false, tie = false;
 
+  // Each list ascends, so only its leading entries can beat the current k-th best: one ballot
+  // finds how many are worth offering (ties with the k-th best included, they raise `tie`).
   for (int li = (prev_ids ? -1 : 0); li < a.n_lists; li++) {
     const u32 *ids = li < 0 ? prev_ids + x * (size_t)k : lists_ids + ((size_t)li * n + x) * k;
     const FT *dist = li < 0 ? prev_dist + x * (size_t)k : lists_dist + ((size_t)li * n + x) * k;
@@ -48,12 +50,20 @@ merge_lists_kernel(const u32 *__restrict__ lists_ids, const FT *__restrict__ lis
       int e = base + lane;
       FT mv = e < admit ? dist[e] : ft_inf();
       u32 mi = e < admit ? ids[e] : sentinel;
-      int cnt = min(32, admit - base);
-      for (int j = 0; j < cnt; j++) {
+      unsigned fin = __ballot_sync(FULL, e < admit && mv != ft_inf());
+      if (__ballot_sync(FULL, e < admit && mv == ft_inf())) any_inf = true;
+      if (fin) {                                               // largest finite entry of this run
+        int last = 31 - __clz(fin);
+        FT lv = __shfl_sync(FULL, mv, last);
+        u32 lid = __shfl_sync(FULL, mi, last);
+        if (lv > max_v) { max_v = lv; max_id = lid; }
+      }
+      unsigned pass = __ballot_sync(FULL, e < admit && mv <= tau && mv != ft_inf());
+      while (pass) {
+        int j = __ffs(pass) - 1;
+        pass &= pass - 1;
         FT vn = __shfl_sync(FULL, mv, j);
         u32 idn = __shfl_sync(FULL, mi, j);
-        if (vn == ft_inf()) { any_inf = true; continue; }
-        if (vn > max_v) { max_v = vn; max_id = idn; }
         consider<R>(best, tau, vn, idn, k, sentinel, lane, tie);
       }
     }

@@ -129,6 +129,62 @@ __device__ __forceinline__ FT tile_sqdist(const FT (&q)[D], const FT *crow) {
   return v[0];
 }
 
+#ifdef USE_FLOAT
+// Packed FP32x2 arithmetic (Blackwell FADD2 / FFMA2): two IEEE round-to-nearest results per
+// instruction, i.e. the same bits as the scalar operations at half the issue slots.
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 even under -fmad=false, which
+// would change the rounding; so the square is written as an explicit fma with a -0.0 addend
+// (x*x + (-0.0) rounds exactly like x*x), leaving no multiply for the adds to absorb.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// nz must hold (-0.0f, -0.0f) and must NOT be a compile-time constant: ptxas would turn the
+// fma back into a multiply and contract it with the next add.  It arrives as a kernel argument.
+__device__ __forceinline__ f32x2 sqr2(f32x2 a, f32x2 nz) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(a), "l"(nz));
+  return r;
+}
+
+// Same tree as TreeNode/tile_sqdist on pairs: P_LEN[i] = P_2LEN[i] + P_2LEN[i + LEN/2],
+// elements (2i, 2i+1) packed; the last level adds the two halves of the remaining pair.
+template <int D, int LEN, int OFF>   // LEN, OFF in elements; node = one 16-byte vector (2 pairs)
+struct PackedNode {
+  static __device__ __forceinline__ void eval(const f32x2 (&q2)[D / 2], const FT *crow, f32x2 nz, f32x2 (&out)[2]) {
+    f32x2 a[2], b[2];
+    PackedNode<D, 2 * LEN, OFF>::eval(q2, crow, nz, a);
+    PackedNode<D, 2 * LEN, OFF + LEN>::eval(q2, crow, nz, b);
+    out[0] = add2(a[0], b[0]);
+    out[1] = add2(a[1], b[1]);
+  }
+};
+template <int D, int OFF>
+struct PackedNode<D, D, OFF> {
+  static __device__ __forceinline__ void eval(const f32x2 (&q2)[D / 2], const FT *crow, f32x2 nz, f32x2 (&out)[2]) {
+    ulonglong2 c = *reinterpret_cast<const ulonglong2 *>(crow + OFF);
+    out[0] = sqr2(sub2(q2[OFF / 2], c.x), nz);
+    out[1] = sqr2(sub2(q2[OFF / 2 + 1], c.y), nz);
+  }
+};
+template <int D>
+__device__ __forceinline__ FT tile_sqdist_packed(const f32x2 (&q2)[D / 2], const FT *crow, f32x2 nz) {
+  f32x2 v[2];
+  PackedNode<D, 4, 0>::eval(q2, crow, nz, v);                          // V_4[0..3] as two pairs
+  f32x2 h = add2(v[0], v[1]);                                       // V_2[0..1]
+  float lo, hi;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(h));
+  return lo + hi;                                                   // V_1[0]
+}
+#endif
+
 #define CE_ASC(da, ia, db, ib)                                    \
   {                                                               \
     bool sw_ = (da) > (db);                                       \
@@ -137,18 +193,18 @@ __device__ __forceinline__ FT tile_sqdist(const FT (&q)[D], const FT *crow) {
     (da) = lo_; (db) = hi_; (ia) = li_; (ib) = hj_;               \
   }
 
-// list <- the KC smallest of list ∪ batch, ascending.  `tie` is raised when the smallest
-// discarded value equals the largest kept one (an exact tie on the boundary).
-template <int KC>
-__device__ __forceinline__ void fold_batch(FT (&ld)[KC], u32 (&li)[KC], FT (&bd)[KC], u32 (&bi)[KC],
+// list <- the KC smallest of list ∪ batch (B <= KC entries), ascending.  `tie` is raised when
+// the smallest discarded value equals the largest kept one (an exact tie on the boundary).
+template <int KC, int B>
+__device__ __forceinline__ void fold_batch(FT (&ld)[KC], u32 (&li)[KC], FT (&bd)[B], u32 (&bi)[B],
                                            bool sort_batch, bool &tie) {
   if (sort_batch) {
 #pragma unroll
-    for (int kk = 2; kk <= KC; kk <<= 1)
+    for (int kk = 2; kk <= B; kk <<= 1)
 #pragma unroll
       for (int j = kk >> 1; j > 0; j >>= 1)
 #pragma unroll
-        for (int i = 0; i < KC; i++) {
+        for (int i = 0; i < B; i++) {
           int l = i ^ j;
           if (l > i) {
             if ((i & kk) == 0) CE_ASC(bd[i], bi[i], bd[l], bi[l])
@@ -156,9 +212,11 @@ __device__ __forceinline__ void fold_batch(FT (&ld)[KC], u32 (&li)[KC], FT (&bd)
           }
         }
   }
+  // the batch, reversed, against the tail of the list: the minima are the KC smallest and
+  // form a bitonic sequence with the untouched head of the list
   FT mdisc = ft_inf();
 #pragma unroll
-  for (int i = 0; i < KC; i++) {
+  for (int i = KC - B; i < KC; i++) {
     FT a = ld[i], b = bd[KC - 1 - i];
     bool tb = b < a;
     mdisc = fmin(mdisc, tb ? a : b);
@@ -187,23 +245,24 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-template <int D, int KC>
+template <int D, int KC, int B>
 struct TileSmem {
   static constexpr int RS = D + VW;                                   // padded row stride
   static constexpr size_t rows_bytes = 2ull * TILE_CH * RS * sizeof(FT);
   static constexpr size_t cid_bytes = 2ull * TILE_CH * sizeof(u32);
-  static constexpr size_t batch_bytes = (size_t)KC * 32 * (sizeof(FT) + sizeof(u32));
+  static constexpr size_t batch_bytes = (size_t)B * 32 * (sizeof(FT) + sizeof(u32));
   static constexpr size_t seg_bytes = (33 + 32) * sizeof(u32);
   static constexpr size_t per_warp = (rows_bytes + cid_bytes + batch_bytes + seg_bytes + 15) & ~(size_t)15;
 };
 
-template <int D, int KC>
-__global__ void __launch_bounds__(TILE_WARPS * 32)
+template <int D, int KC, int B, int MINB>
+__global__ void __launch_bounds__(TILE_WARPS * 32, MINB)
 leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
                       const u32 *__restrict__ offset, const u32 *__restrict__ tmax_p, size_t n,
                       size_t buckets, int d_short, int k, u32 *__restrict__ list_ids,
-                      FT *__restrict__ list_dist, TieList ties, int pack_tries, int max_slices) {
-  typedef TileSmem<D, KC> SM;
+                      FT *__restrict__ list_dist, TieList ties, int pack_tries, int max_slices,
+                      unsigned long long negzero2) {
+  typedef TileSmem<D, KC, B> SM;
   constexpr int RS = SM::RS;
   constexpr int PPR = D / VW;                                          // 16-byte pieces per row
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -211,9 +270,9 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
   unsigned char *mine = smem_raw + (size_t)wib * SM::per_warp;
   FT *rows = reinterpret_cast<FT *>(mine);                             // [2][CH][RS]
   u32 *cids = reinterpret_cast<u32 *>(mine + SM::rows_bytes);          // [2][CH]
-  FT *bdist = reinterpret_cast<FT *>(mine + SM::rows_bytes + SM::cid_bytes);   // [KC][32]
-  u32 *bidx = reinterpret_cast<u32 *>(bdist + KC * 32);                // [KC][32]
-  u32 *segpos = bidx + KC * 32;                                        // [33]
+  FT *bdist = reinterpret_cast<FT *>(mine + SM::rows_bytes + SM::cid_bytes);   // [B][32]
+  u32 *bidx = reinterpret_cast<u32 *>(bdist + B * 32);                 // [B][32]
+  u32 *segpos = bidx + B * 32;                                         // [33]
   u32 *segrow = segpos + 33;                                           // [32]
 
   const size_t b = (size_t)blockIdx.x * TILE_WARPS + wib;
@@ -276,6 +335,18 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
     const size_t my_row = (size_t)beg + qbase + qi;
     const u32 my_id = order[my_row];
 
+#ifdef USE_FLOAT
+    f32x2 q[D / 2];                                                 // the query row, packed pairs
+    {
+      const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(sp + my_row * (size_t)D);
+#pragma unroll
+      for (int v = 0; v < PPR; v++) {
+        ulonglong2 t = src[v];
+        q[2 * v] = t.x;
+        q[2 * v + 1] = t.y;
+      }
+    }
+#else
     FT q[D];
     {
       const Vec16 *src = reinterpret_cast<const Vec16 *>(sp + my_row * (size_t)D);
@@ -286,6 +357,7 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
         for (int w = 0; w < VW; w++) q[v * VW + w] = t.x[w];
       }
     }
+#endif
     FT ld[KC];
     u32 li[KC];
 #pragma unroll
@@ -326,28 +398,44 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
       else cp_async_wait<0>();
       __syncwarp();
       const FT *crows = rows + (size_t)buf * TILE_CH * RS;
-      for (int i = 0; i < per; i++) {
-        const int j = s + S * i;
-        const u32 cid = cids[buf * TILE_CH + j];
-        FT dist = tile_sqdist<D>(q, crows + j * RS);
-        if (cid == sentinel || cid == my_id) dist = ft_inf();        // pad / self (compute.cl:144-149)
-        bdist[cnt * 32 + lane] = dist;
-        bidx[cnt * 32 + lane] = cid;
-        cnt++;
-      }
-      if (cnt + per > KC || c + 1 == nchunks) {
-        FT bd[KC];
-        u32 bi[KC];
-#pragma unroll
-        for (int i = 0; i < KC; i++) {
-          bool have = i < cnt;
-          bd[i] = have ? bdist[i * 32 + lane] : ft_inf();
-          bi[i] = have ? bidx[i * 32 + lane] : sentinel;
+      // runs of candidates between flushes: the inner loop is distance + append only
+      for (int i = 0; i < per;) {
+        const int run = min(per - i, B - cnt);
+        for (int e = 0; e < run; e++, i++) {
+          const int j = s + S * i;
+          const u32 cid = cids[buf * TILE_CH + j];
+#ifdef USE_FLOAT
+          FT dist = tile_sqdist_packed<D>(q, crows + j * RS, negzero2);
+#else
+          FT dist = tile_sqdist<D>(q, crows + j * RS);
+#endif
+          if (cid == sentinel || cid == my_id) dist = ft_inf();      // pad / self (compute.cl:144-149)
+          bdist[cnt * 32 + lane] = dist;
+          bidx[cnt * 32 + lane] = cid;
+          cnt++;
         }
-        fold_batch<KC>(ld, li, bd, bi, true, tie);
-        cnt = 0;
+        if (cnt == B) {                                              // cnt is warp-uniform
+          FT bd[B];
+          u32 bi[B];
+#pragma unroll
+          for (int e = 0; e < B; e++) { bd[e] = bdist[e * 32 + lane]; bi[e] = bidx[e * 32 + lane]; }
+          fold_batch<KC, B>(ld, li, bd, bi, true, tie);
+          cnt = 0;
+        }
       }
       __syncwarp();
+    }
+    if (cnt > 0) {
+      FT bd[B];
+      u32 bi[B];
+#pragma unroll
+      for (int e = 0; e < B; e++) {
+        bool have = e < cnt;
+        bd[e] = have ? bdist[e * 32 + lane] : ft_inf();
+        bi[e] = have ? bidx[e * 32 + lane] : sentinel;
+      }
+      fold_batch<KC, B>(ld, li, bd, bi, true, tie);
+      cnt = 0;
     }
     // fold the slices of each query together (lists are sorted: no batch sort needed)
     for (int sc = S; sc > 1;) {
@@ -363,7 +451,7 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
       }
       bool other_tie = __shfl_sync(FULL, (int)tie, src);
       if (s + hs < sc) {
-        fold_batch<KC>(ld, li, bd, bi, false, tie);
+        fold_batch<KC, KC>(ld, li, bd, bi, false, tie);
         tie |= other_tie;
       }
       sc = hs;
@@ -487,14 +575,14 @@ static void launch_warp_r(int regs, dim3 grid, dim3 block, size_t smem, annb_str
 #undef WARP_CASE
 }
 
-template <int D, int KC>
+template <int D, int KC, int B, int MINB>
 static void launch_tile(annb_stream stream, const FT *sp, const u32 *order, const u32 *offset,
                         const u32 *tmax, size_t n, size_t buckets, int d_short, int k, u32 *ids,
                         FT *dist, TieList flags) {
-  size_t smem = TileSmem<D, KC>::per_warp * TILE_WARPS;
+  size_t smem = TileSmem<D, KC, B>::per_warp * TILE_WARPS;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(leaf_topk_tile_kernel<D, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(leaf_topk_tile_kernel<D, KC, B, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
   unsigned grid = (unsigned)((buckets + TILE_WARPS - 1) / TILE_WARPS);
@@ -507,7 +595,7 @@ static void launch_tile(annb_stream stream, const FT *sp, const u32 *order, cons
     if (max_slices < 1) max_slices = 1;
     if (max_slices > 16) max_slices = 16;
   }
-  leaf_topk_tile_kernel<D, KC><<<grid, TILE_WARPS * 32, smem, stream>>>(sp, order, offset, tmax, n, buckets, d_short, k, ids, dist, flags, pack_tries, max_slices);
+  leaf_topk_tile_kernel<D, KC, B, MINB><<<grid, TILE_WARPS * 32, smem, stream>>>(sp, order, offset, tmax, n, buckets, d_short, k, ids, dist, flags, pack_tries, max_slices, 0x8000000080000000ull);
 }
 
 // returns false when no tiled instantiation covers (d, k)
@@ -517,18 +605,26 @@ static bool try_launch_tile(annb_stream stream, const FT *sp, const u32 *order, 
   const char *off = getenv("ANN_B200_NO_TILE");
   if (off && *off && *off != '0') return false;
   if (d_short > 31) return false;
-#define TILE_CASE(DD, KK) { launch_tile<DD, KK>(stream, sp, order, offset, tmax, n, buckets, d_short, (int)k, ids, dist, flags); return true; }
+#define TILE_CASE(DD, KK, BB, MB) { launch_tile<DD, KK, BB, MB>(stream, sp, order, offset, tmax, n, buckets, d_short, (int)k, ids, dist, flags); return true; }
   if (k <= 16) {
-    if (d == 16) TILE_CASE(16, 16)
-    if (d == 32) TILE_CASE(32, 16)
+    if (d == 16) TILE_CASE(16, 16, 16, 3)
+    if (d == 32) TILE_CASE(32, 16, 16, 3)
 #ifdef USE_FLOAT
-    if (d == 64) TILE_CASE(64, 16)
+    if (d == 64) {
+      static int variant = -1;
+      if (variant < 0) { const char *e = getenv("ANN_B200_TILE_VARIANT"); variant = e && *e ? atoi(e) : 0; }
+      if (variant == 1) TILE_CASE(64, 16, 8, 3)
+      if (variant == 2) TILE_CASE(64, 16, 8, 4)
+      if (variant == 3) TILE_CASE(64, 16, 16, 4)
+      if (variant == 4) TILE_CASE(64, 16, 4, 3)
+      TILE_CASE(64, 16, 16, 3)
+    }
 #endif
   }
 #ifdef USE_FLOAT
   else if (k <= 32) {
-    if (d == 16) TILE_CASE(16, 32)
-    if (d == 32) TILE_CASE(32, 32)
+    if (d == 16) TILE_CASE(16, 32, 32, 2)
+    if (d == 32) TILE_CASE(32, 32, 32, 2)
   }
 #endif
 #undef TILE_CASE
