@@ -209,11 +209,11 @@ _loaded = {}
 
 
 class StageTimes(ctypes.Structure):
-    _fields_ = [("ms", ctypes.c_float * 7)]
+    _fields_ = [("ms", ctypes.c_float * 9)]
 
 
-STAGE_NAMES = ("upload", "means", "hash", "lists_first_group", "lists_rest", "supercharge",
-               "download")
+STAGE_NAMES = ("upload", "means", "hash", "buckets", "leaf", "exchange", "merge", "supercharge",
+               "first_to_last_event")
 
 
 def gpu_backend(dtype) -> Backend:

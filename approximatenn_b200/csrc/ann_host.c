@@ -44,6 +44,7 @@ void annh_fatal(const char *fmt, const char *detail) {
   } while (0)
 
 typedef struct hook { void (*f)(void); struct hook *next; } hook;
+#define ANNH_MAX_SPANS 1024
 
 static struct {
   int ready;
@@ -55,7 +56,9 @@ static struct {
   size_t arena_bytes, arena_used;
   annh_stage_times last;
   int timing;
-  cudaEvent_t ev[ANNH_STAGES + 1];
+  cudaEvent_t ev[2 * ANNH_MAX_SPANS];
+  int span_stage[ANNH_MAX_SPANS];
+  int spans;
 } G;
 
 void gpu_init(void) {
@@ -73,7 +76,7 @@ void gpu_init(void) {
   CK(cudaSetDevice(dev));
   G.device = dev;
   CK(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
-  for (int i = 0; i <= ANNH_STAGES; i++) CK(cudaEventCreate(&G.ev[i]));
+  for (int i = 0; i < 2 * ANNH_MAX_SPANS; i++) CK(cudaEventCreate(&G.ev[i]));
   const char *tm = getenv("ANN_B200_TIMING");
   G.timing = tm && *tm && *tm != '0';
   G.ready = 1;
@@ -99,7 +102,7 @@ void gpu_cleanup(void) {
   if (G.arena) CK(cudaFree(G.arena));
   G.arena = NULL;
   G.arena_bytes = G.arena_used = 0;
-  for (int i = 0; i <= ANNH_STAGES; i++) CK(cudaEventDestroy(G.ev[i]));
+  for (int i = 0; i < 2 * ANNH_MAX_SPANS; i++) CK(cudaEventDestroy(G.ev[i]));
   CK(cudaStreamDestroy(G.stream));
   G.ready = 0;
 }
@@ -265,15 +268,29 @@ static void projection_rows(const host_transform *t, size_t rots_b, size_t len_b
 /* ------------------------------------------------------------------------------------ */
 /* stage timing (CUDA events on the library stream; off unless asked for)                */
 
-static void mark(int i) { if (G.timing) CK(cudaEventRecord(G.ev[i], G.stream)); }
-
+/* a span = [begin, end) event pair on the library stream, attributed to one stage          */
+static int span_begin(int stage) {
+  if (!G.timing || G.spans >= ANNH_MAX_SPANS) return -1;
+  int id = G.spans++;
+  G.span_stage[id] = stage;
+  CK(cudaEventRecord(G.ev[2 * id], G.stream));
+  return id;
+}
+static void span_end(int id) {
+  if (id >= 0) CK(cudaEventRecord(G.ev[2 * id + 1], G.stream));
+}
 static void collect_times(void) {
-  if (!G.timing) return;
-  for (int i = 0; i < ANNH_STAGES; i++) {
+  memset(&G.last, 0, sizeof G.last);
+  if (!G.timing || G.spans == 0) { G.spans = 0; return; }
+  for (int i = 0; i < G.spans; i++) {
     float ms = 0;
-    CK(cudaEventElapsedTime(&ms, G.ev[i], G.ev[i + 1]));
-    G.last.ms[i] = ms;
+    CK(cudaEventElapsedTime(&ms, G.ev[2 * i], G.ev[2 * i + 1]));
+    G.last.ms[G.span_stage[i]] += ms;
   }
+  float total = 0;
+  CK(cudaEventElapsedTime(&total, G.ev[0], G.ev[2 * (G.spans - 1) + 1]));
+  G.last.ms[ANNH_STAGES - 1] = total;
+  G.spans = 0;
 }
 
 /* host wall-clock checkpoints (ANN_B200_HOSTPROF=1 prints them to stderr)                */
@@ -419,7 +436,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
 
   HP("arena");
   /* 3. upload: the whole set, or this rank's rows followed by an all-gather over NVLink   */
-  mark(0);
+  int sp = span_begin(0);
   if (my_rows)
     CK(cudaMemcpyAsync(dX + row_lo * d, points + row_lo * d, my_rows * d * w, cudaMemcpyHostToDevice, st));
   if (sharded) annh_dist_allgather_rows(dX, n, d * w, st);
@@ -433,15 +450,17 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
 
   HP("upload enqueued");
   /* 4. S0 column means (alg.c:367-368); the accumulator borrows the sorted-copy buffer */
-  mark(1);
+  span_end(sp);
+  sp = span_begin(1);
   annb_fold_rows(dX, dXs, n, d, 1, st);
   for (size_t len = n >> 1; len >> 1; len >>= 1) annb_fold_rows(dXs, dXs, len, d, 0, st);
   annb_scale_means(dXs, n, d, dmean, st);
 
   /* 5. S1 hashes of every owned try in one pass over the points                         */
-  mark(2);
+  span_end(sp);
+  sp = span_begin(2);
   if (Tl) annb_hash_points(dX, dmean, &desc, dhash, dhscratch, st);
-  mark(3);
+  span_end(sp);
 
   if (save) {
     save->tries = tries; save->n = n; save->k = k; save->d_short = d_short; save->d_long = d;
@@ -474,6 +493,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
     for (size_t j = 0; j < g; j++) {
       size_t t = own[j0 + j];
       const annb_u32 *hash_t = dhash + (j0 + j) * n;
+      sp = span_begin(3);
       annb_build_buckets(hash_t, n, buckets, dcount, doffset, dorder_tmp, dorder, dtmax + t, dscan, st);
       if (save) {                                  /* padded table for save->which_par[t] */
         annb_u32 tm = 0;
@@ -491,38 +511,46 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
         CK(cudaMemcpyAsync(save->which_par[t], dtable, cells * sizeof(size_t), cudaMemcpyDeviceToHost, st));
       }
       annb_gather_rows(dX, dorder, n, d, dXs, st);
+      span_end(sp);
+      sp = span_begin(4);
       annb_leaf_topk(dXs, dorder, doffset, hash_t, dtmax + t, n, d, d_short, k, dl_ids + j * n * k,
                      dl_dist + j * n * k, dscratch, dstatus, st);
+      span_end(sp);
       admit[j] = annb200_dist_admit(k, tries, (int)t);
     }
     if (!sharded) {
       int whole = group == Tl;                     /* corner + literal redo need every list */
+      sp = span_begin(6);
       annb_merge_lists(dl_ids, dl_dist, (int)g, admit, whole ? corner_list : -1, corner_pos,
                        have_merged ? dm_ids : NULL, have_merged ? dm_dist : NULL, n, n, k, whole,
                        dm_ids2, dm_dist2, dscratch, scratch_bytes, dstatus, st);
       annb_u32 *ti = dm_ids; dm_ids = dm_ids2; dm_ids2 = ti;
       ftype *td = dm_dist; dm_dist = dm_dist2; dm_dist2 = td;
       have_merged = 1;
+      span_end(sp);
     }
-    if (j0 == 0) mark(4);
   }
-  if (Tl == 0) mark(4);
   if (dtable) { CK(cudaStreamSynchronize(st)); CK(cudaFree(dtable)); }
 
   HP("tries enqueued");
   /* 6b. sharded: every list goes to the owner of its rows, who merges all T of them       */
   const ftype *own_dist_base = dm_dist;            /* indexed with GLOBAL row numbers       */
   if (sharded) {
+    sp = span_begin(5);
     annh_dist_exchange_lists(dl_ids, ds_ids, n, k * 4, tries, st);
     annh_dist_exchange_lists(dl_dist, ds_dist, n, k * w, tries, st);
+    span_end(sp);
+    sp = span_begin(6);
     for (size_t t = 0; t < T; t++) admit[t] = annb200_dist_admit(k, tries, (int)t);
     if (my_rows)
       annb_merge_lists(ds_ids, ds_dist, tries, admit, corner_list, corner_pos, NULL, NULL, my_rows, n,
                        k, 1, dm_ids + row_lo * k, dm_dist2, dscratch, scratch_bytes, dstatus, st);
+    span_end(sp);
+    sp = span_begin(5);
     annh_dist_allgather_rows(dm_ids, n, k * 4, st);   /* neighbours' lists for supercharging */
+    span_end(sp);
     own_dist_base = dm_dist2 - row_lo * k;
   }
-  mark(5);
 
   /* 7. S5 supercharging of the owned rows (alg.c:313-327); graph = the merged lists        */
   {
@@ -530,8 +558,10 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
     for (int c = 0; c < nch; c++) {
       size_t r0 = row_lo + ((my_rows * (size_t)c / nch) & ~(size_t)31);
       size_t r1 = c + 1 == nch ? row_hi : row_lo + ((my_rows * (size_t)(c + 1) / nch) & ~(size_t)31);
+      sp = span_begin(7);
       annb_supercharge(dX, dX, dm_ids, own_dist_base, dm_ids, n, d, k, r0, r1, 1, dout_ids + r0 * k,
                        dout_dist + r0 * k, dscratch, scratch_bytes, dstatus, st);
+      span_end(sp);
       if (!(full_result && sharded))
         annh_egress_chunk(eg, r0 - row_lo, r1 - row_lo, dout_ids + r0 * k, dout_dist + r0 * k, st);
     }
@@ -541,7 +571,6 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
       annh_egress_chunk(eg, 0, n, dout_ids, dout_dist, st);
     }
   }
-  mark(6);
 
   HP("supercharge enqueued");
   /* 8. results: the egress threads are already widening the first chunks                 */
@@ -549,7 +578,6 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   int h_status = 0;
   CK(cudaMemcpyAsync(h_tmax, dtmax, 4 * T, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(&h_status, dstatus, sizeof(int), cudaMemcpyDeviceToHost, st));
-  mark(7);
   CK(cudaStreamSynchronize(st));
   HP("stream drained");
   collect_times();

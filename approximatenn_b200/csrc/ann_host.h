@@ -23,11 +23,13 @@ int annh_device(void);
 void annh_arena_reserve(size_t bytes);
 void *annh_arena_take(size_t bytes);
 
-/* Device-time of the stages of the last precomp_gpu call, measured with CUDA events on
- * the library stream when timing is on (annh_set_timing(1) or ANN_B200_TIMING=1).
- *   0 upload  1 means  2 hash  3 buckets+leaf lists (first merge group)  4 remaining groups
- *   5 supercharge  6 download                                                            */
-#define ANNH_STAGES 7
+/* Device time per stage of the last precomp_gpu call, summed over tries / chunks, measured
+ * with CUDA events on the library stream when timing is on (annh_set_timing(1) or
+ * ANN_B200_TIMING=1):
+ *   0 upload (H2D + point all-gather)  1 means  2 hash  3 bucket tables + sorted copy
+ *   4 leaf lists (S3 incl. literal redo)  5 list exchange (sharded only)  6 merge
+ *   7 supercharge (incl. literal redo)  8 total from first to last event                    */
+#define ANNH_STAGES 9
 typedef struct { float ms[ANNH_STAGES]; } annh_stage_times;
 const annh_stage_times *annh_last_times(void);
 void annh_set_timing(int on);

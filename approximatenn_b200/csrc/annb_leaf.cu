@@ -14,6 +14,13 @@
 #include "annb_common.cuh"
 
 static __device__ unsigned long long leaf_literal_rows_dev;
+static __device__ unsigned long long leaf_pairs_dev;      // (point, real candidate) pairs measured by S3
+extern "C" unsigned long long annb_leaf_pairs(int reset) {
+  unsigned long long v = 0, z = 0;
+  cudaMemcpyFromSymbol(&v, leaf_pairs_dev, sizeof v);
+  if (reset) cudaMemcpyToSymbol(leaf_pairs_dev, &z, sizeof z);
+  return v;
+}
 unsigned long long annb_leaf_literal_count(int reset) {
   unsigned long long v = 0, z = 0;
   cudaMemcpyFromSymbol(&v, leaf_literal_rows_dev, sizeof v);
@@ -50,6 +57,7 @@ leaf_topk_warp_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
   best.clear(sentinel);
   FT tau = ft_inf();
   bool tie = false;
+  unsigned npairs = 0;
 
   for (int y = 0; y <= d_short; y++) {
     unsigned long long first_slot = (unsigned long long)y * tmax;
@@ -70,8 +78,10 @@ leaf_topk_warp_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
         dist = generic_sqdist(qrow, sp + row * (size_t)d, d, tmp, lane);
       }
       consider<R>(best, tau, dist, order[row], k, sentinel, lane, tie);
+      npairs++;
     }
   }
+  if (lane == 0) atomicAdd(&leaf_pairs_dev, (unsigned long long)npairs);
 #pragma unroll
   for (int rr = 0; rr < R; rr++) {
     int p = rr * 32 + lane;
@@ -177,7 +187,7 @@ struct PackedNode<D, D, OFF> {
 template <int D>
 __device__ __forceinline__ FT tile_sqdist_packed(const f32x2 (&q2)[D / 2], const FT *crow, f32x2 nz) {
   f32x2 v[2];
-  PackedNode<D, 4, 0>::eval(q2, crow, nz, v);                          // V_4[0..3] as two pairs
+  PackedNode<D, 4, 0>::eval(q2, crow, nz, v);                      // V_4[0..3] as two pairs
   f32x2 h = add2(v[0], v[1]);                                       // V_2[0..1]
   float lo, hi;
   asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(h));
@@ -307,6 +317,7 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
   }
   __syncwarp();
   const u32 C = segpos[32];
+  if (lane == 0) atomicAdd(&leaf_pairs_dev, (unsigned long long)Q * (C - 1));   // self excluded
 
   // Queries are packed as (query, slice): S slices of the candidate stream per query, so that
   // Qp*S lanes work.  The bucket is cut into `passes` groups of qpp queries where that

@@ -244,16 +244,19 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     gpu.lib.annb_launch_count(1)
+    gpu.lib.annb_leaf_pairs.restype = ctypes.c_ulonglong
+    gpu.lib.annb_leaf_pairs(1)
     barrier()
     t0 = time.perf_counter()
     stages = [step() for _ in range(args.steps)]
     barrier()
     wall = time.perf_counter() - t0
     launches = int(gpu.lib.annb_launch_count(0))
+    leaf_pairs = int(gpu.lib.annb_leaf_pairs(0)) / args.steps        # per step, this rank
     sampler.stop_flag.set()
     sampler.join()
 
-    dev_keys = ("means", "hash", "lists_first_group", "lists_rest", "supercharge")
+    dev_keys = ("means", "hash", "buckets", "leaf", "exchange", "merge", "supercharge")
     dev_ms = [sum(s[k_] for k_ in dev_keys) for s in stages]
     dev_total_s = sum(dev_ms) / 1e3
     if world > 1:
@@ -271,16 +274,31 @@ def main():
     w = np.dtype(dtype).itemsize
     mean_stage = {k_: statistics.mean(s[k_] for s in stages) for k_ in stages[0]}
     peak, peak_src = measured_peaks()
-    # dominant HBM-bound kernel: supercharge.  Algorithmic bytes per launch:
+    dev_mean = statistics.mean(dev_ms)
+    # --- dominant kernel: leaf_topk_tile_kernel (S3), FP32-pipe bound.  Algorithmic work per
+    # (point, candidate) pair = d subtractions + d multiplications + d-1 additions, each rounded
+    # separately (the reference's arithmetic, compute.cl:147-166; an FMA would change its bits),
+    # counted as 3*d flops.  Peak = one rounded FP32 operation per lane per clock:
+    # 148 SMs x 128 lanes x max SM clock (half of the usual FFMA-counts-two figure).
+    leaf_s = mean_stage["leaf"] / 1e3
+    fp32_peak = 148 * 128 * 1.965e9 / 1e12
+    leaf_tflops = 3 * d * leaf_pairs / leaf_s / 1e12 if leaf_s > 0 else 0.0
+    roofline = {"kernel": "leaf_topk_tile_kernel (S3, summed over the tries of one step; includes its literal redo)",
+                "bound": "fp32", "achieved": leaf_tflops, "peak": fp32_peak,
+                "peak_source": "148 SM x 128 lanes x 1.965 GHz, one separately rounded FP32 op per lane-clock",
+                "unit": "TFLOP/s", "frac": leaf_tflops / fp32_peak, "traffic": None,
+                "pairs_per_step": leaf_pairs, "flops_per_pair": 3 * d,
+                "share_of_device_time": mean_stage["leaf"] / dev_mean}
+    # --- dominant HBM-bound kernel: supercharge.  Algorithmic bytes per launch set:
     # rows*(P2-k) gathered vectors of (4 + d*w) B, + own lists in, + ids and dists out.
     P2 = 1 << ((k * (k + 1)).bit_length() - 1)
     rows = n / world                      # supercharge rows per rank
     sc_bytes = rows * (P2 - k) * (4 + d * w) + rows * k * (4 + w) + rows * k * (4 + w)
     sc_s = mean_stage["supercharge"] / 1e3
-    roofline = {"kernel": "supercharge_kernel", "bound": "hbm", "achieved": sc_bytes / sc_s / 1e9,
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": sc_bytes / sc_s / 1e9 / peak, "traffic": None,
-                "share_of_device_time": mean_stage["supercharge"] / statistics.mean(dev_ms)}
+    roofline_hbm = {"kernel": "supercharge_fast_kernel (S5, all row chunks of one step)", "bound": "hbm",
+                    "achieved": sc_bytes / sc_s / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": sc_bytes / sc_s / 1e9 / peak, "traffic": None,
+                    "share_of_device_time": mean_stage["supercharge"] / dev_mean}
     line = {"metric": METRIC, "value": n * args.steps / dev_total_s, "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_total_s / args.steps, "higher_is_better": True,
@@ -290,7 +308,7 @@ def main():
             "e2e": {"value": n * args.steps / wall, "unit": "points/s",
                     "h2d_bytes_per_step": n * d * w, "d2h_bytes_per_step": n * k * (4 + w),
                     "ms_per_step": 1e3 * wall / args.steps},
-            "gpu_launches": launches, "stage_ms": mean_stage, "roofline": roofline,
+            "gpu_launches": launches, "stage_ms": mean_stage, "roofline": roofline, "roofline_hbm": roofline_hbm,
             "clocks": sampler.summary()}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, pts, args.cpu_sample)

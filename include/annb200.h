@@ -146,6 +146,10 @@ void annb_query_rows(const ftype *y, const ftype *points, const annb_u32 *const 
                      int *status, annb_stream stream);
 void annb_narrow_ids(const size_t *src, size_t count, annb_u32 *dst, annb_stream stream);
 
+/* (point, real candidate) pairs whose distance S3 evaluated since the last reset (synchronous);
+ * 3*d floating-point operations each (compute.cl:147-166) — the flop count of the leaf stage     */
+unsigned long long annb_leaf_pairs(int reset);
+
 /* rows redone by the literal kernels since the last reset: [0] S3, [1] S4, [2] S5 (synchronous)  */
 void annb_literal_rows(unsigned long long out[3], int reset);
 
