@@ -621,15 +621,7 @@ static bool try_launch_tile(annb_stream stream, const FT *sp, const u32 *order, 
     if (d == 16) TILE_CASE(16, 16, 16, 3)
     if (d == 32) TILE_CASE(32, 16, 16, 3)
 #ifdef USE_FLOAT
-    if (d == 64) {
-      static int variant = -1;
-      if (variant < 0) { const char *e = getenv("ANN_B200_TILE_VARIANT"); variant = e && *e ? atoi(e) : 0; }
-      if (variant == 1) TILE_CASE(64, 16, 8, 3)
-      if (variant == 2) TILE_CASE(64, 16, 8, 4)
-      if (variant == 3) TILE_CASE(64, 16, 16, 4)
-      if (variant == 4) TILE_CASE(64, 16, 4, 3)
-      TILE_CASE(64, 16, 16, 3)
-    }
+    if (d == 64) TILE_CASE(64, 16, 16, 3)
 #endif
   }
 #ifdef USE_FLOAT

@@ -86,7 +86,7 @@ class ClockSampler(threading.Thread):
             for name, bit in self.REASONS:
                 if mask & bit:
                     self.reasons.add(name)
-            self.stop_flag.wait(0.02)
+            self.stop_flag.wait(0.1)
 
     def _smi(self):
         self.how = "nvidia-smi"
@@ -139,6 +139,35 @@ def cpu_baseline(cfg, pts, sample_points):
             "detail": {k_: float(v) for k_, v in c.items()}}
 
 
+def measure_recall(gpu, pts, cfg, sample):
+    """recall@k of one more (untimed) precomp against exact brute force on `sample` points.
+    The brute force is measurement harness only: fp32 torch matmul on the GPU, top-(k+1) minus self."""
+    import torch
+    from approximatenn_b200.api import srandom, _libc, _view
+    n, d, k, tries, dtype = cfg
+    dptr = ctypes.c_void_p()
+    srandom(1001)
+    ids_p = gpu.precomp_raw(n, k, d, pts.ctypes.data, tries, *ROT, None, ctypes.byref(dptr))
+    ids = _view(ids_p, (n, k), np.uint64)
+    rng = np.random.default_rng(5)
+    rows = np.sort(rng.choice(n, size=min(sample, n), replace=False))
+    X = torch.from_numpy(np.ascontiguousarray(pts)).cuda().to(torch.float32)
+    q = X[torch.from_numpy(rows).cuda()]
+    xn = (X * X).sum(1)
+    hits = 0
+    for i in range(0, len(rows), 256):
+        qq = q[i:i + 256]
+        d2 = (qq * qq).sum(1, keepdim=True) + xn[None, :] - 2.0 * qq @ X.T
+        d2[torch.arange(len(qq)), torch.from_numpy(rows[i:i + 256]).cuda()] = float("inf")
+        exact = d2.topk(k, dim=1, largest=False).indices.cpu().numpy()
+        got = ids[rows[i:i + 256]].astype(np.int64)
+        hits += sum(len(np.intersect1d(a, b)) for a, b in zip(exact, got))
+    _libc.free(ids_p)
+    _libc.free(dptr)
+    return {"recall_at_k": hits / (len(rows) * k), "k": k, "sample_points": int(len(rows)),
+            "against": "exact brute force (fp32) over all n points"}
+
+
 def run_reference_arm(args, cfg, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -181,6 +210,8 @@ def main():
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--cpu-sample", type=int, default=256, help="points in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--recall-sample", type=int, default=2000,
+                    help="points whose exact k nearest neighbours are brute-forced for recall@k (0 = skip)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     n, d, k, tries, dtype = cfg
@@ -246,13 +277,24 @@ def main():
     gpu.lib.annb_launch_count(1)
     gpu.lib.annb_leaf_pairs.restype = ctypes.c_ulonglong
     gpu.lib.annb_leaf_pairs(1)
+    # timed region 1: K steps with per-stage CUDA events on the library stream -> `value`
     barrier()
     t0 = time.perf_counter()
     stages = [step() for _ in range(args.steps)]
     barrier()
-    wall = time.perf_counter() - t0
+    wall_instrumented = time.perf_counter() - t0
     launches = int(gpu.lib.annb_launch_count(0))
     leaf_pairs = int(gpu.lib.annb_leaf_pairs(0)) / args.steps        # per step, this rank
+    # timed region 2: the same K steps through the C-ABI with the event instrumentation off -> `e2e`
+    gpu.lib.annh_set_timing(0)
+    step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    barrier()
+    wall = time.perf_counter() - t0
+    gpu.lib.annh_set_timing(1)
     sampler.stop_flag.set()
     sampler.join()
 
@@ -307,9 +349,12 @@ def main():
             "config": workload_config(cfg, args.config, world),
             "e2e": {"value": n * args.steps / wall, "unit": "points/s",
                     "h2d_bytes_per_step": n * d * w, "d2h_bytes_per_step": n * k * (4 + w),
-                    "ms_per_step": 1e3 * wall / args.steps},
+                    "ms_per_step": 1e3 * wall / args.steps,
+                    "ms_per_step_with_stage_events": 1e3 * wall_instrumented / args.steps},
             "gpu_launches": launches, "stage_ms": mean_stage, "roofline": roofline, "roofline_hbm": roofline_hbm,
             "clocks": sampler.summary()}
+    if args.recall_sample > 0 and world == 1:
+        line["recall"] = measure_recall(gpu, pts, cfg, args.recall_sample)
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, pts, args.cpu_sample)
     sys.stdout.flush()
