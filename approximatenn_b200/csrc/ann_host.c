@@ -404,8 +404,13 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
                  pad256(Tl * planes * 2 * 4 + 4) + pad256(Tl * planes * 2 * w + w) +
                  pad256(Tl * d_max * 4 + 4) + pad256(Tl * d_short * 4 + 4) +
                  pad256(annb_hash_scratch_bytes(&desc)) +
-                 pad256(n * k * 4) * 3 + pad256(n * k * w) * 3 + pad256(scratch_bytes) + 8192;
-  if (sharded) fixed += pad256(T * my_rows * k * 4) + pad256(T * my_rows * k * w);
+                 pad256(scratch_bytes) + 8192;
+  if (sharded)   /* merged ids (all rows), merged dists + results (own rows), exchanged lists */
+    fixed += pad256(n * k * 4) + pad256(my_rows * k * w) + pad256(my_rows * k * 4) + pad256(my_rows * k * w) +
+             pad256(T * my_rows * k * 4) + pad256(T * my_rows * k * w) +
+             (full_result ? pad256(n * k * 4) + pad256(n * k * w) : 0);
+  else
+    fixed += pad256(n * k * 4) * 3 + pad256(n * k * w) * 3;
   size_t group = Tl ? Tl : 1;                                  /* lists kept before a merge */
   while (!sharded && group > 1 && fixed + group * list_bytes + 512 > free_b * 9 / 10) group--;
   if ((size_t)k * T < 16) group = Tl ? Tl : 1;
@@ -423,10 +428,16 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   void *dhscratch = annh_arena_take(annb_hash_scratch_bytes(&desc));
   annb_u32 *dl_ids = annh_arena_take(group * n * k * 4);
   ftype *dl_dist = annh_arena_take(group * n * k * w);
-  annb_u32 *dm_ids = annh_arena_take(n * k * 4), *dm_ids2 = annh_arena_take(n * k * 4);
-  ftype *dm_dist = annh_arena_take(n * k * w), *dm_dist2 = annh_arena_take(n * k * w);
-  annb_u32 *dout_ids = annh_arena_take(n * k * 4);
-  ftype *dout_dist = annh_arena_take(n * k * w);
+  /* merged lists: ids for all rows (the graph S5 walks); distances for the owned rows only.
+   * Single GPU: two sets, ping-ponged by the grouped merge.  out_*: result rows, indexed from
+   * out_base (0 when the whole result is assembled here, row_lo when only the owned rows are). */
+  const size_t out_base = (sharded && !full_result) ? row_lo : 0;
+  const size_t out_cap = (sharded && !full_result) ? my_rows : n;
+  annb_u32 *dm_ids = annh_arena_take(n * k * 4), *dm_ids2 = sharded ? NULL : annh_arena_take(n * k * 4);
+  ftype *dm_dist = sharded ? NULL : annh_arena_take(n * k * w);
+  ftype *dm_dist2 = annh_arena_take((sharded ? my_rows : n) * k * w);
+  annb_u32 *dout_ids = annh_arena_take(out_cap * k * 4);
+  ftype *dout_dist = annh_arena_take(out_cap * k * w);
   void *dscratch = annh_arena_take(scratch_bytes);
   int *dstatus = annh_arena_take(sizeof(int));
   annb_u32 *ds_ids = sharded ? annh_arena_take(T * my_rows * k * 4) : NULL;   /* [T][my_rows][k] */
@@ -559,11 +570,13 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
       size_t r0 = row_lo + ((my_rows * (size_t)c / nch) & ~(size_t)31);
       size_t r1 = c + 1 == nch ? row_hi : row_lo + ((my_rows * (size_t)(c + 1) / nch) & ~(size_t)31);
       sp = span_begin(7);
-      annb_supercharge(dX, dX, dm_ids, own_dist_base, dm_ids, n, d, k, r0, r1, 1, dout_ids + r0 * k,
-                       dout_dist + r0 * k, dscratch, scratch_bytes, dstatus, st);
+      annb_supercharge(dX, dX, dm_ids, own_dist_base, dm_ids, n, d, k, r0, r1, 1,
+                       dout_ids + (r0 - out_base) * k, dout_dist + (r0 - out_base) * k, dscratch,
+                       scratch_bytes, dstatus, st);
       span_end(sp);
       if (!(full_result && sharded))
-        annh_egress_chunk(eg, r0 - row_lo, r1 - row_lo, dout_ids + r0 * k, dout_dist + r0 * k, st);
+        annh_egress_chunk(eg, r0 - row_lo, r1 - row_lo, dout_ids + (r0 - out_base) * k,
+                          dout_dist + (r0 - out_base) * k, st);
     }
     if (full_result && sharded) {                  /* every rank ends up with all rows      */
       annh_dist_allgather_rows(dout_ids, n, k * 4, st);

@@ -88,8 +88,9 @@ static void *egress_worker(void *p) {
       if (hi > lo) b[(hi - lo) * sizeof(ftype) - 1] = 0;
     }
   }
-  /* 2. chunks me, me+nthreads, ...: wait for the copy stream, widen ids, copy distances */
-  for (int c = me;; c += e->nthreads) {
+  /* 2. every chunk, as it lands: this thread widens/copies its 1/nthreads share of the rows,
+   *    so the tail after the last chunk is short                                            */
+  for (int c = 0;; c++) {
     pthread_mutex_lock(&e->mu);
     while (c >= e->submitted && !e->closed) pthread_cond_wait(&e->cv, &e->mu);
     int have = c < e->submitted;
@@ -100,7 +101,9 @@ static void *egress_worker(void *p) {
       fprintf(stderr, "approximatenn_b200: result copy failed: %s\n", cudaGetErrorString(cudaGetLastError()));
       exit(1);
     }
-    size_t lo = ch->r0 * e->k, hi = ch->r1 * e->k;
+    size_t rows = ch->r1 - ch->r0;
+    size_t lo = (ch->r0 + rows * (size_t)me / e->nthreads) * e->k;
+    size_t hi = (ch->r0 + rows * (size_t)(me + 1) / e->nthreads) * e->k;
     const annb_u32 *src = e->stage_ids;
     size_t *dst = e->ids;
     for (size_t i = lo; i < hi; i++) dst[i] = src[i];
