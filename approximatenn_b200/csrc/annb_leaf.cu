@@ -99,7 +99,7 @@ leaf_topk_warp_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
 
 static constexpr int VW = 16 / sizeof(FT);          // elements per 16-byte vector
 static constexpr int TILE_CH = 16;                  // candidate rows per staged chunk
-static constexpr int TILE_WARPS = 4;
+static constexpr int TILE_WARPS = 1;            // one bucket per CTA: a finished bucket frees its registers at once
 
 struct __align__(16) Vec16 { FT x[VW]; };
 
@@ -265,13 +265,13 @@ struct TileSmem {
   static constexpr size_t per_warp = (rows_bytes + cid_bytes + batch_bytes + seg_bytes + 15) & ~(size_t)15;
 };
 
-template <int D, int KC, int B, int MINB>
-__global__ void __launch_bounds__(TILE_WARPS * 32, MINB)
+template <int D, int KC, int B, int REGS>
+__global__ void __maxnreg__(REGS)
 leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
                       const u32 *__restrict__ offset, const u32 *__restrict__ tmax_p, size_t n,
                       size_t buckets, int d_short, int k, u32 *__restrict__ list_ids,
                       FT *__restrict__ list_dist, TieList ties, int pack_tries, int max_slices,
-                      unsigned long long negzero2) {
+                      unsigned long long negzero2, u32 *__restrict__ ticket) {
   typedef TileSmem<D, KC, B> SM;
   constexpr int RS = SM::RS;
   constexpr int PPR = D / VW;                                          // 16-byte pieces per row
@@ -285,11 +285,16 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
   u32 *segpos = bidx + B * 32;                                         // [33]
   u32 *segrow = segpos + 33;                                           // [32]
 
-  const size_t b = (size_t)blockIdx.x * TILE_WARPS + wib;
+  const u32 sentinel = (u32)n;
+  // persistent warps: buckets are handed out by an atomic ticket, so a warp that drew a light
+  // bucket immediately takes another one
+  for (;;) {
+  size_t b = 0;
+  if (lane == 0) b = atomicAdd(ticket, 1u);
+  b = __shfl_sync(FULL, (u32)b, 0);
   if (b >= buckets) return;
   const u32 beg = offset[b], Q = offset[b + 1] - beg;
-  if (Q == 0) return;
-  const u32 sentinel = (u32)n;
+  if (Q == 0) continue;
   const unsigned long long tmax = *tmax_p;
   const unsigned long long L = (unsigned long long)(d_short + 1) * tmax;
   const unsigned long long P = 1ull << floor_log2_u(L);
@@ -479,6 +484,7 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
     }
     __syncwarp();
   }
+  }   // next ticket
 }
 
 // =====================================================================================
@@ -586,17 +592,26 @@ static void launch_warp_r(int regs, dim3 grid, dim3 block, size_t smem, annb_str
 #undef WARP_CASE
 }
 
-template <int D, int KC, int B, int MINB>
+template <int D, int KC, int B, int REGS>
 static void launch_tile(annb_stream stream, const FT *sp, const u32 *order, const u32 *offset,
                         const u32 *tmax, size_t n, size_t buckets, int d_short, int k, u32 *ids,
                         FT *dist, TieList flags) {
   size_t smem = TileSmem<D, KC, B>::per_warp * TILE_WARPS;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(leaf_topk_tile_kernel<D, KC, B, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(leaf_topk_tile_kernel<D, KC, B, REGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
   unsigned grid = (unsigned)((buckets + TILE_WARPS - 1) / TILE_WARPS);
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    unsigned resident = (unsigned)sms * 16;                 // more CTAs than can be resident: all SMs stay full
+    if (grid > resident) grid = resident;
+  }
+  u32 *ticket = flags.count + 32;                           // spare words of the tie-list header
+  cudaMemsetAsync(ticket, 0, sizeof(u32), stream);
   static int pack_tries = -1, max_slices = 16;
   if (pack_tries < 0) {
     const char *e1 = getenv("ANN_B200_TILE_PASSES"), *e2 = getenv("ANN_B200_TILE_SLICES");
@@ -606,7 +621,7 @@ static void launch_tile(annb_stream stream, const FT *sp, const u32 *order, cons
     if (max_slices < 1) max_slices = 1;
     if (max_slices > 16) max_slices = 16;
   }
-  leaf_topk_tile_kernel<D, KC, B, MINB><<<grid, TILE_WARPS * 32, smem, stream>>>(sp, order, offset, tmax, n, buckets, d_short, k, ids, dist, flags, pack_tries, max_slices, 0x8000000080000000ull);
+  leaf_topk_tile_kernel<D, KC, B, REGS><<<grid, TILE_WARPS * 32, smem, stream>>>(sp, order, offset, tmax, n, buckets, d_short, k, ids, dist, flags, pack_tries, max_slices, 0x8000000080000000ull, ticket);
 }
 
 // returns false when no tiled instantiation covers (d, k)
@@ -618,16 +633,16 @@ static bool try_launch_tile(annb_stream stream, const FT *sp, const u32 *order, 
   if (d_short > 31) return false;
 #define TILE_CASE(DD, KK, BB, MB) { launch_tile<DD, KK, BB, MB>(stream, sp, order, offset, tmax, n, buckets, d_short, (int)k, ids, dist, flags); return true; }
   if (k <= 16) {
-    if (d == 16) TILE_CASE(16, 16, 16, 3)
-    if (d == 32) TILE_CASE(32, 16, 16, 3)
+    if (d == 16) TILE_CASE(16, 16, 16, 128)
+    if (d == 32) TILE_CASE(32, 16, 16, 128)
 #ifdef USE_FLOAT
-    if (d == 64) TILE_CASE(64, 16, 16, 3)
+    if (d == 64) TILE_CASE(64, 16, 16, 168)      // 12 resident warps/SM; lower caps spill and lose (profiles/)
 #endif
   }
 #ifdef USE_FLOAT
   else if (k <= 32) {
-    if (d == 16) TILE_CASE(16, 32, 32, 2)
-    if (d == 32) TILE_CASE(32, 32, 32, 2)
+    if (d == 16) TILE_CASE(16, 32, 32, 168)
+    if (d == 32) TILE_CASE(32, 32, 32, 200)
   }
 #endif
 #undef TILE_CASE
