@@ -83,6 +83,112 @@ merge_lists_kernel(const u32 *__restrict__ lists_ids, const FT *__restrict__ lis
   if (tie && ties.rows && lane == 0) tie_report(ties, (u32)x);
 }
 
+// Fast union for k <= 16: the running result sits ascending in lanes 0-15, the next list is
+// loaded DEscending into lanes 16-31, so the warp holds a bitonic sequence and five xor-shuffle
+// compare-exchange steps sort all 32 entries; equal ids (always adjacent: equal ids have equal
+// distances) are dropped and the first k distinct entries are compacted back into lanes 0-15.
+__global__ void __launch_bounds__(256)
+merge_lists_fast_kernel(const u32 *__restrict__ lists_ids, const FT *__restrict__ lists_dist,
+                        MergeArgs a, size_t n, u32 sentinel, int k, u32 *__restrict__ out_ids,
+                        FT *__restrict__ out_dist, TieList ties) {
+  const int lane = threadIdx.x & 31;
+  size_t x = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (x >= n) return;
+  const int e = lane & 15;
+  FT v = ft_inf();
+  u32 id = sentinel;
+  FT max_v = -ft_inf();
+  u32 max_id = sentinel;
+  bool any_inf = false, tie = false;
+
+  // list li: ascending into lanes 0-15 for li == 0, descending into lanes 16-31 afterwards;
+  // the loads of list li+1 are issued before list li is merged (one list of latency hidden)
+  auto fetch = [&](int li, FT &fv, u32 &fi) {
+    fv = ft_inf();
+    fi = sentinel;
+    if (li >= a.n_lists) return;
+    const bool mine = li == 0 ? lane < 16 : lane >= 16;
+    const int src = li == 0 ? e : 15 - e;
+    if (mine && src < a.admit[li]) {
+      fv = lists_dist[((size_t)li * n + x) * k + src];
+      fi = lists_ids[((size_t)li * n + x) * k + src];
+    }
+  };
+  FT nxt_v, nxt_v2;
+  u32 nxt_i, nxt_i2;
+  fetch(0, nxt_v, nxt_i);
+  fetch(1, nxt_v2, nxt_i2);
+  for (int li = 0; li < a.n_lists; li++) {
+    const int admit = a.admit[li];
+    const bool mine = li == 0 ? lane < 16 : lane >= 16;
+    const int src = li == 0 ? e : 15 - e;
+    FT nv = nxt_v;
+    u32 ni = nxt_i;
+    nxt_v = nxt_v2; nxt_i = nxt_i2;
+    fetch(li + 2, nxt_v2, nxt_i2);
+    if (__ballot_sync(FULL, mine && src < admit && nv == ft_inf())) any_inf = true;
+    {
+      // largest finite admitted entry of this list (prefix-corner rule)
+      FT cv = (mine && nv != ft_inf()) ? nv : -ft_inf();
+      u32 ci = ni;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        FT ov = __shfl_xor_sync(FULL, cv, o);
+        u32 oi = __shfl_xor_sync(FULL, ci, o);
+        if (ov > cv) { cv = ov; ci = oi; }
+      }
+      if (cv > max_v) { max_v = cv; max_id = ci; }
+    }
+    if (mine) { v = nv; id = ni; }
+    if (li == 0) {
+      if (lane >= 16) { v = ft_inf(); id = sentinel; }
+      if (a.n_lists > 1) continue;
+    }
+    // bitonic merge of the 32 lanes (ascending)
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+      FT pv = __shfl_xor_sync(FULL, v, j);
+      u32 pi = __shfl_xor_sync(FULL, id, j);
+      bool low = (lane & j) == 0;
+      bool take = low ? (pv < v) : (pv > v);
+      if (take) { v = pv; id = pi; }
+    }
+    // duplicates, ties, compaction of the first k distinct entries
+    FT pv = __shfl_up_sync(FULL, v, 1);
+    u32 pi = __shfl_up_sync(FULL, id, 1);
+    bool finite = v != ft_inf();
+    bool dup = lane > 0 && finite && id == pi;
+    unsigned uniq = __ballot_sync(FULL, finite && !dup);
+    int rank = __popc(uniq & ((1u << lane) - 1));                 // distinct entries before this lane
+    // an equal-distance pair of different ids whose earlier member is kept (rank-1 < k)
+    bool eqpair = lane > 0 && finite && !dup && v == pv && rank >= 1 && rank - 1 < k;
+    if (__any_sync(FULL, eqpair)) tie = true;
+    int want = lane;                                              // lane r takes the r-th distinct entry
+    int from = (want < k && want < __popc(uniq)) ? (int)__fns(uniq, 0, want + 1) : -1;
+    FT gv = __shfl_sync(FULL, v, from < 0 ? 0 : from);
+    u32 gi = __shfl_sync(FULL, id, from < 0 ? 0 : from);
+    v = from < 0 ? ft_inf() : gv;
+    id = from < 0 ? sentinel : gi;
+  }
+  if (a.corner_list >= 0 && !any_inf) {
+    u32 cid = lists_ids[((size_t)a.corner_list * n + x) * k + a.corner_pos];
+    if (cid == max_id) {                                          // drop it, close the gap
+      unsigned hit = __ballot_sync(FULL, id == cid && v != ft_inf());
+      if (hit) {
+        int pos = __ffs(hit) - 1;
+        FT nv = __shfl_down_sync(FULL, v, 1);
+        u32 ni = __shfl_down_sync(FULL, id, 1);
+        if (lane >= pos) { v = lane == 31 ? ft_inf() : nv; id = lane == 31 ? sentinel : ni; }
+      }
+    }
+  }
+  if (lane < k) {
+    out_ids[x * (size_t)k + lane] = id;
+    out_dist[x * (size_t)k + lane] = v;
+  }
+  if (tie && ties.rows && lane == 0) tie_report(ties, (u32)x);
+}
+
 // Literal row: the n_lists lists of a point side by side (k*n_lists slots), the reference's
 // network, first k slots out.  One CTA per reported row (ties.rows == NULL: every row — rows
 // shorter than 16 slots).
@@ -145,6 +251,10 @@ extern "C" void annb_merge_lists(const u32 *lists_ids, const FT *lists_dist, int
   if (whole_row) cudaMemsetAsync(ls.list.count, 0, sizeof(u32), stream);
   TieList f = whole_row ? ls.list : all_rows;        // rows == NULL: ties are not recorded
   dim3 block(256), grid(grid_for(n * 32, 256));
+  const char *nofast = getenv("ANN_B200_NO_FAST_MERGE");
+  if (k <= 16 && merged_in_ids == NULL && !(nofast && *nofast && *nofast != '0')) {
+    merge_lists_fast_kernel<<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, n, (u32)sentinel_n, (int)k, merged_ids, merged_dist, f);
+  } else
   switch (regs) {
     case 1: merge_lists_kernel<1><<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, merged_in_ids, merged_in_dist, n, (u32)sentinel_n, (int)k, merged_ids, merged_dist, f); break;
     case 2: merge_lists_kernel<2><<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, merged_in_ids, merged_in_dist, n, (u32)sentinel_n, (int)k, merged_ids, merged_dist, f); break;
