@@ -36,6 +36,7 @@ static struct {
   int (*CommDestroy)(ncclComm_t);
   int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
   int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
   int (*GroupStart)(void);
   int (*GroupEnd)(void);
   const char *(*GetErrorString)(int);
@@ -68,6 +69,7 @@ static void load_nccl(void) {
   SYM(CommDestroy, "ncclCommDestroy");
   SYM(Send, "ncclSend");
   SYM(Recv, "ncclRecv");
+  SYM(AllGather, "ncclAllGather");
   SYM(GroupStart, "ncclGroupStart");
   SYM(GroupEnd, "ncclGroupEnd");
   SYM(GetErrorString, "ncclGetErrorString");
@@ -117,11 +119,21 @@ int annh_dist_gather_results(void) { return D.gather; }
 
 int annb200_dist_try_owner(int t, int world) { return t % world; }
 
-/* rows [lo, hi) owned by `rank`: equal cuts rounded down to a multiple of 32 rows          */
-void annb200_dist_slice(size_t n, int rank, int world, size_t *lo, size_t *hi) {
-  *lo = (n * (size_t)rank / (size_t)world) & ~(size_t)31;
-  *hi = rank + 1 == world ? n : (n * (size_t)(rank + 1) / (size_t)world) & ~(size_t)31;
+/* rows [lo, hi) owned by `rank`: equal slices of S = ceil(n/world) rounded up to 32 rows (the
+ * last ones may be short or empty), so that row arrays can be all-gathered in place with one
+ * ncclAllGather of S rows per rank into a buffer padded to world*S rows                      */
+static size_t slice_rows(size_t n, int world) {
+  size_t s = (n + (size_t)world - 1) / (size_t)world;
+  return (s + 31) & ~(size_t)31;
 }
+void annb200_dist_slice(size_t n, int rank, int world, size_t *lo, size_t *hi) {
+  size_t s = slice_rows(n, world);
+  size_t a = s * (size_t)rank, b = a + s;
+  *lo = a < n ? a : n;
+  *hi = b < n ? b : n;
+}
+/* rows a buffer must hold to be all-gathered in place */
+size_t annh_dist_padded_rows(size_t n) { return D.world > 1 ? slice_rows(n, D.world) * (size_t)D.world : n; }
 
 /* entries of try t that fall inside the sorted prefix of the merged row */
 int annb200_dist_admit(size_t k, int tries, int t) {
@@ -137,23 +149,13 @@ int annb200_dist_admit(size_t k, int tries, int t) {
 
 /* ---- exchange steps (all on `stream`) --------------------------------------------------- */
 
-/* every rank contributes rows [lo(r), hi(r)) of a [n][row_bytes] array; afterwards all
- * ranks hold all rows                                                                       */
+/* every rank contributes its slice of a row array (capacity annh_dist_padded_rows(n) rows);
+ * afterwards all ranks hold all rows.  In-place ncclAllGather: NVLink/NVSwitch at full rate. */
 void annh_dist_allgather_rows(void *base, size_t n, size_t row_bytes, void *stream) {
   if (D.world == 1) return;
-  size_t mylo, myhi;
-  annb200_dist_slice(n, D.rank, D.world, &mylo, &myhi);
-  NCK(D.GroupStart());
-  for (int p = 0; p < D.world; p++) {
-    if (p == D.rank) continue;
-    size_t lo, hi;
-    annb200_dist_slice(n, p, D.world, &lo, &hi);
-    if (myhi > mylo)
-      NCK(D.Send((char *)base + mylo * row_bytes, (myhi - mylo) * row_bytes, NCCL_UINT8, p, D.comm, (cudaStream_t)stream));
-    if (hi > lo)
-      NCK(D.Recv((char *)base + lo * row_bytes, (hi - lo) * row_bytes, NCCL_UINT8, p, D.comm, (cudaStream_t)stream));
-  }
-  NCK(D.GroupEnd());
+  size_t s = slice_rows(n, D.world);
+  NCK(D.AllGather((const char *)base + (size_t)D.rank * s * row_bytes, base, s * row_bytes, NCCL_UINT8,
+                  D.comm, (cudaStream_t)stream));
 }
 
 /* all-to-all of per-try lists: `local` holds this rank's tries as [local_try][n][row_bytes];

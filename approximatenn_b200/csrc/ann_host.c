@@ -394,11 +394,12 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   desc.tries = (int)Tl;
   desc.inv_sqrt2 = 1 / sqrt(2.0);
   const size_t list_bytes = n * k * (4 + w);                   /* one per-try list      */
+  const size_t np = annh_dist_padded_rows(n);                  /* rows of all-gathered arrays */
   const size_t scratch_bytes = annb_leaf_scratch_bytes(n);
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   free_b += G.arena_bytes;
-  size_t fixed = pad256(n * d * w) * 2 + pad256(d * w) + pad256(Tl * n * 4 + 4) +
+  size_t fixed = pad256(np * d * w) + pad256(n * d * w) + pad256(d * w) + pad256(Tl * n * 4 + 4) +
                  pad256(buckets * 4) + pad256((buckets + 1) * 4) + pad256(n * 4) * 2 +
                  pad256(T * 4) + pad256(annb_scan_tmp_bytes(buckets)) +
                  pad256(Tl * planes * 2 * 4 + 4) + pad256(Tl * planes * 2 * w + w) +
@@ -406,9 +407,9 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
                  pad256(annb_hash_scratch_bytes(&desc)) +
                  pad256(scratch_bytes) + 8192;
   if (sharded)   /* merged ids (all rows), merged dists + results (own rows), exchanged lists */
-    fixed += pad256(n * k * 4) + pad256(my_rows * k * w) + pad256(my_rows * k * 4) + pad256(my_rows * k * w) +
+    fixed += pad256(np * k * 4) + pad256(my_rows * k * w) + pad256(my_rows * k * 4) + pad256(my_rows * k * w) +
              pad256(T * my_rows * k * 4) + pad256(T * my_rows * k * w) +
-             (full_result ? pad256(n * k * 4) + pad256(n * k * w) : 0);
+             (full_result ? pad256(np * k * 4) + pad256(np * k * w) : 0);
   else
     fixed += pad256(n * k * 4) * 3 + pad256(n * k * w) * 3;
   size_t group = Tl ? Tl : 1;                                  /* lists kept before a merge */
@@ -416,7 +417,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   if ((size_t)k * T < 16) group = Tl ? Tl : 1;
   annh_arena_reserve(fixed + group * list_bytes + 512);
 
-  ftype *dX = annh_arena_take(n * d * w), *dXs = annh_arena_take(n * d * w), *dmean = annh_arena_take(d * w);
+  ftype *dX = annh_arena_take(np * d * w), *dXs = annh_arena_take(n * d * w), *dmean = annh_arena_take(d * w);
   annb_u32 *dhash = annh_arena_take(Tl * n * 4 + 4);
   annb_u32 *dcount = annh_arena_take(buckets * 4), *doffset = annh_arena_take((buckets + 1) * 4);
   annb_u32 *dorder_tmp = annh_arena_take(n * 4), *dorder = annh_arena_take(n * 4);
@@ -432,8 +433,8 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
    * Single GPU: two sets, ping-ponged by the grouped merge.  out_*: result rows, indexed from
    * out_base (0 when the whole result is assembled here, row_lo when only the owned rows are). */
   const size_t out_base = (sharded && !full_result) ? row_lo : 0;
-  const size_t out_cap = (sharded && !full_result) ? my_rows : n;
-  annb_u32 *dm_ids = annh_arena_take(n * k * 4), *dm_ids2 = sharded ? NULL : annh_arena_take(n * k * 4);
+  const size_t out_cap = (sharded && !full_result) ? my_rows : np;
+  annb_u32 *dm_ids = annh_arena_take(np * k * 4), *dm_ids2 = sharded ? NULL : annh_arena_take(n * k * 4);
   ftype *dm_dist = sharded ? NULL : annh_arena_take(n * k * w);
   ftype *dm_dist2 = annh_arena_take((sharded ? my_rows : n) * k * w);
   annb_u32 *dout_ids = annh_arena_take(out_cap * k * 4);

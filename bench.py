@@ -40,6 +40,7 @@ CONFIGS = {
     "cfg2": (65536, 32, 16, 8, np.float64),
     "cfg3": (1_000_000, 64, 16, 8, np.float32),
     "cfg4": (10_000_000, 64, 16, 8, np.float32),
+    "cfg5": (100_000_000, 32, 32, 8, np.float32),        # needs 8 GPUs (sharded)
 }
 ROT = (6, 1, 1, 1)          # reference defaults (time_results.c:16-17)
 METRIC = "all-points kNN points/sec (precomp: hash + per-try lists + merge + supercharge)"

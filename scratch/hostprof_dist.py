@@ -5,7 +5,7 @@ from approximatenn_b200.api import gpu_backend, srandom, _libc
 from approximatenn_b200 import dist as adist
 local = int(os.environ.get("LOCAL_RANK", "0")); torch.cuda.set_device(local); os.environ["ANN_B200_DEVICE"] = str(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-cfg = bench.CONFIGS["cfg3"]; n, d, k, tries, dtype = cfg
+cfg = bench.CONFIGS[os.environ.get("CFG", "cfg3")]; n, d, k, tries, dtype = cfg
 host = torch.empty((n, d), dtype=torch.float32, pin_memory=True); pts = host.numpy(); pts[:] = bench.synth_points(n, d, dtype)
 gpu = gpu_backend(dtype); gpu.lib.gpu_init(); adist.init_from_torch(gpu.lib)
 def run(tag):
