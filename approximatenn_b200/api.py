@@ -8,8 +8,8 @@ behaviour (the C library prints to stderr and exits, /root/reference/gpu_comp.c:
 `Backend` is deliberately generic over the shared library and the symbol names, so that
 the same class binds
   * the product:  libann_b200_f32.so / libann_b200_f64.so  (precomp_gpu, query_gpu)
-  * the checkers: oracle/liboracle_*.so, oracle/_ref/libannref_*.so  (tests only)
-Nothing in this module knows about the oracle.
+  * any other library with the same two entry points (the test suite binds its CPU checkers
+    through this class; nothing in this package loads or knows them).
 """
 from __future__ import annotations
 
