@@ -396,9 +396,6 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   const size_t list_bytes = n * k * (4 + w);                   /* one per-try list      */
   const size_t np = annh_dist_padded_rows(n);                  /* rows of all-gathered arrays */
   const size_t scratch_bytes = annb_leaf_scratch_bytes(n);
-  size_t free_b = 0, total_b = 0;
-  CK(cudaMemGetInfo(&free_b, &total_b));
-  free_b += G.arena_bytes;
   size_t fixed = pad256(np * d * w) + pad256(n * d * w) + pad256(d * w) + pad256(Tl * n * 4 + 4) +
                  pad256(buckets * 4) + pad256((buckets + 1) * 4) + pad256(n * 4) * 2 +
                  pad256(T * 4) + pad256(annb_scan_tmp_bytes(buckets)) +
@@ -413,7 +410,14 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   else
     fixed += pad256(n * k * 4) * 3 + pad256(n * k * w) * 3;
   size_t group = Tl ? Tl : 1;                                  /* lists kept before a merge */
-  while (!sharded && group > 1 && fixed + group * list_bytes + 512 > free_b * 9 / 10) group--;
+  if (!sharded && fixed + group * list_bytes + 512 > G.arena_bytes) {
+    /* the arena has to grow: see what the device can give (cudaMemGetInfo costs milliseconds,
+     * so it is not asked when the cached arena already fits the whole plan)                  */
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    free_b += G.arena_bytes;
+    while (group > 1 && fixed + group * list_bytes + 512 > free_b * 9 / 10) group--;
+  }
   if ((size_t)k * T < 16) group = Tl ? Tl : 1;
   annh_arena_reserve(fixed + group * list_bytes + 512);
 
