@@ -39,27 +39,36 @@ def _run(cmd, verbose):
 
 
 def build(force: bool = False, verbose: bool = False) -> None:
+    """Compile (in parallel) whatever is stale, then link the two libraries."""
+    from concurrent.futures import ThreadPoolExecutor
+
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    jobs, links = [], []
     for suffix, defs in (("f32", ["-DUSE_FLOAT"]), ("f64", [])):
         objs = []
         for src in CU_SOURCES:
             obj = os.path.join(HERE, "build", f"{os.path.splitext(src)[0]}_{suffix}.o")
             path = os.path.join(CSRC, src)
             if force or _stale(obj, [path] + HEADERS):
-                _run([NVCC, *ARCH, "-O3", "-lineinfo", "-fmad=false", "-std=c++17", *defs,
-                      "-I", INCLUDE, "-I", CSRC, "-Xcompiler", "-fPIC", "-c", path, "-o", obj], verbose)
+                jobs.append([NVCC, *ARCH, "-O3", "-lineinfo", "-fmad=false", "-std=c++17", *defs,
+                             "-I", INCLUDE, "-I", CSRC, "-Xcompiler", "-fPIC", "-c", path, "-o", obj])
             objs.append(obj)
         for src in C_SOURCES:
             obj = os.path.join(HERE, "build", f"{os.path.splitext(src)[0]}_{suffix}.o")
             path = os.path.join(CSRC, src)
             if force or _stale(obj, [path] + HEADERS):
-                _run(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-Wall", "-Wextra", *defs,
-                      "-I", INCLUDE, "-I", CSRC, "-I", os.path.join(CUDA_HOME, "include"),
-                      "-c", path, "-o", obj], verbose)
+                jobs.append(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-Wall", "-Wextra", *defs,
+                             "-I", INCLUDE, "-I", CSRC, "-I", os.path.join(CUDA_HOME, "include"),
+                             "-c", path, "-o", obj])
             objs.append(obj)
-        out = lib_path(suffix)
-        if force or _stale(out, objs):
-            _run([NVCC, *ARCH, "-shared", "-Xlinker", "-Bsymbolic", "-o", out, *objs, "-lcudart", "-lm", "-lpthread", "-ldl"], verbose)
+        links.append((lib_path(suffix), objs))
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+            list(pool.map(lambda cmd: _run(cmd, verbose), jobs))
+    for out, objs in links:
+        if force or jobs or _stale(out, objs):
+            _run([NVCC, *ARCH, "-shared", "-Xlinker", "-Bsymbolic", "-o", out, *objs,
+                  "-lcudart", "-lm", "-lpthread", "-ldl"], verbose)
 
 
 if __name__ == "__main__":

@@ -54,6 +54,8 @@ static struct {
   /* one device arena reused across calls; grown on demand, released by gpu_cleanup()  */
   char *arena;
   size_t arena_bytes, arena_used;
+  size_t *table_buf;           /* staging for exported bucket tables, grown geometrically  */
+  size_t table_cap;
   annh_stage_times last;
   int timing;
   cudaEvent_t ev[2 * ANNH_MAX_SPANS];
@@ -99,6 +101,9 @@ void gpu_cleanup(void) {
   }
   CK(cudaStreamSynchronize(G.stream));
   annh_egress_release();
+  if (G.table_buf) CK(cudaFree(G.table_buf));
+  G.table_buf = NULL;
+  G.table_cap = 0;
   if (G.arena) CK(cudaFree(G.arena));
   G.arena = NULL;
   G.arena_bytes = G.arena_used = 0;
@@ -500,8 +505,6 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
     corner_pos = (int)(prefix % k);
   }
   int have_merged = 0;
-  size_t *dtable = NULL;
-  size_t dtable_cap = 0;
   int admit[64];
   for (size_t j0 = 0; j0 < Tl; j0 += group) {
     size_t g = Tl - j0 < group ? Tl - j0 : group;
@@ -516,11 +519,12 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
         CK(cudaMemcpyAsync(&tm, dtmax + t, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         size_t cells = buckets * (size_t)tm;
-        if (cells > dtable_cap) {
-          if (dtable) CK(cudaFree(dtable));
-          CK(cudaMalloc((void **)&dtable, (cells ? cells : 1) * sizeof(size_t)));
-          dtable_cap = cells;
+        if (cells > G.table_cap) {
+          if (G.table_buf) CK(cudaFree(G.table_buf));
+          G.table_cap = cells + cells / 2 + 1024;
+          CK(cudaMalloc((void **)&G.table_buf, G.table_cap * sizeof(size_t)));
         }
+        size_t *dtable = G.table_buf;
         annb_export_table(doffset, dorder, n, buckets, tm, dtable, st);
         save->par_maxes[t] = tm;
         save->which_par[t] = malloc((cells ? cells : 1) * sizeof(size_t));
@@ -546,7 +550,6 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
       span_end(sp);
     }
   }
-  if (dtable) { CK(cudaStreamSynchronize(st)); CK(cudaFree(dtable)); }
 
   HP("tries enqueued");
   /* 6b. sharded: every list goes to the owner of its rows, who merges all T of them       */
