@@ -101,6 +101,7 @@ void gpu_cleanup(void) {
   }
   CK(cudaStreamSynchronize(G.stream));
   annh_egress_release();
+  annh_ingest_release();
   if (G.table_buf) CK(cudaFree(G.table_buf));
   G.table_buf = NULL;
   G.table_cap = 0;
@@ -458,8 +459,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   HP("arena");
   /* 3. upload: the whole set, or this rank's rows followed by an all-gather over NVLink   */
   int sp = span_begin(0);
-  if (my_rows)
-    CK(cudaMemcpyAsync(dX + row_lo * d, points + row_lo * d, my_rows * d * w, cudaMemcpyHostToDevice, st));
+  if (my_rows) annh_ingest(dX + row_lo * d, points + row_lo * d, my_rows * d * w, st, G.device);
   if (sharded) annh_dist_allgather_rows(dX, n, d * w, st);
   if (planes && Tl) {
     CK(cudaMemcpyAsync(d_idx, h_idx, Tl * planes * 2 * 4, cudaMemcpyHostToDevice, st));

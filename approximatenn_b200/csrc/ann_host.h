@@ -53,6 +53,11 @@ void annh_dist_allgather_rows(void *base, size_t n, size_t row_bytes, void *stre
 void annh_dist_exchange_lists(const void *local, void *slice, size_t n, size_t row_bytes, int tries,
                               void *stream);
 
+/* host -> device upload of caller memory (ann_ingest.c): staged through pinned slots by a few
+ * host threads when the source is pageable                                                 */
+void annh_ingest(void *dst, const void *src, size_t bytes, void *consumer_stream, int device);
+void annh_ingest_release(void);
+
 /* drops any device-resident copy of `save` kept for query_gpu (called by free_save)      */
 void annh_forget_save(const save_t *save);
 

@@ -107,7 +107,7 @@ static void build_index(const save_t *s, const ftype *points, uint64_t fp) {
   }
   size_t *tmp = NULL;
   CK(cudaMalloc((void **)&tmp, tmp_cells * sizeof(size_t)));
-  CK(cudaMemcpyAsync(IDX.d_points, points, s->n * s->d_long * w, cudaMemcpyHostToDevice, st));
+  annh_ingest(IDX.d_points, points, s->n * s->d_long * w, st, annh_device());
   CK(cudaMemcpyAsync(IDX.d_mean, s->row_means, s->d_long * w, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(IDX.d_bases, s->bases, T * s->d_short * s->d_long * w, cudaMemcpyHostToDevice, st));
   upload_narrow(s->graph, s->n * s->k, IDX.d_graph, tmp, st);
