@@ -237,6 +237,25 @@ def gpu_backend(dtype) -> Backend:
     return _loaded[dt]
 
 
+def save_to_file(b: Backend, save: Save, path: str) -> None:
+    """include/annb200_io.h ann_save_write()."""
+    b.lib.ann_save_write.argtypes = [ctypes.POINTER(SaveT), ctypes.c_char_p]
+    b.lib.ann_save_write.restype = ctypes.c_int
+    if b.lib.ann_save_write(ctypes.byref(save.c), os.fsencode(path)) != 0:
+        raise OSError(f"could not write {path}")
+
+
+def save_from_file(b: Backend, path: str) -> Save:
+    """include/annb200_io.h ann_save_read(); the result is released with free_save as usual."""
+    b.lib.ann_save_read.argtypes = [ctypes.POINTER(SaveT), ctypes.c_char_p]
+    b.lib.ann_save_read.restype = ctypes.c_int
+    s = Save(b)
+    if b.lib.ann_save_read(ctypes.byref(s.c), os.fsencode(path)) != 0:
+        raise OSError(f"could not read {path} (missing, truncated, or written by the other ftype build)")
+    s._live = True
+    return s
+
+
 def stage_times(b: Backend) -> dict:
     t = b.lib.annh_last_times().contents
     return {name: float(t.ms[i]) for i, name in enumerate(STAGE_NAMES)}

@@ -15,6 +15,8 @@
  *   4. all-gather(v) of the merged ids (supercharging reads the neighbours' lists)
  *   5. supercharging of the owned rows; the result rows stay with their owner unless
  *      annb200_dist_gather(1) asks every rank to end up with the full result
+ *   save != NULL: the hashes of all tries are broadcast, every rank rebuilds all bucket tables
+ *      (cheap) and gathers the full graph, so each rank ends up with a complete save_t
  */
 #include <dlfcn.h>
 #include <stdio.h>
@@ -37,6 +39,7 @@ static struct {
   int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
   int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
   int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
+  int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
   int (*GroupStart)(void);
   int (*GroupEnd)(void);
   const char *(*GetErrorString)(int);
@@ -70,6 +73,7 @@ static void load_nccl(void) {
   SYM(Send, "ncclSend");
   SYM(Recv, "ncclRecv");
   SYM(AllGather, "ncclAllGather");
+  SYM(Broadcast, "ncclBroadcast");
   SYM(GroupStart, "ncclGroupStart");
   SYM(GroupEnd, "ncclGroupEnd");
   SYM(GetErrorString, "ncclGetErrorString");
@@ -156,6 +160,12 @@ void annh_dist_allgather_rows(void *base, size_t n, size_t row_bytes, void *stre
   size_t s = slice_rows(n, D.world);
   NCK(D.AllGather((const char *)base + (size_t)D.rank * s * row_bytes, base, s * row_bytes, NCCL_UINT8,
                   D.comm, (cudaStream_t)stream));
+}
+
+/* in-place broadcast of `bytes` at `buf` from rank `root` */
+void annh_dist_broadcast(void *buf, size_t bytes, int root, void *stream) {
+  if (D.world == 1) return;
+  NCK(D.Broadcast(buf, buf, bytes, NCCL_UINT8, root, D.comm, (cudaStream_t)stream));
 }
 
 /* all-to-all of per-try lists: `local` holds this rank's tries as [local_try][n][row_bytes];

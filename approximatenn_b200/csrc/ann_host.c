@@ -357,9 +357,8 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   const size_t my_rows = row_hi - row_lo;
   size_t Tl = 0;                                               /* tries owned by this rank  */
   for (size_t t = 0; t < T; t++) Tl += annb200_dist_try_owner((int)t, R) == rank;
-  if (sharded && save) annh_fatal("%s", "save != NULL is not supported in sharded mode yet");
   if (sharded && T > 64) annh_fatal("%s", "more than 64 tries in sharded mode");
-  const int full_result = !sharded || annh_dist_gather_results();
+  const int full_result = !sharded || annh_dist_gather_results() || save != NULL;
   const size_t out_rows = full_result ? n : my_rows;
   annh_egress *eg = annh_egress_begin(out_rows, k, dists_o != NULL, G.device);
 
@@ -409,6 +408,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
                  pad256(Tl * d_max * 4 + 4) + pad256(Tl * d_short * 4 + 4) +
                  pad256(annb_hash_scratch_bytes(&desc)) +
                  pad256(scratch_bytes) + 8192;
+  if (sharded && save) fixed += pad256(T * n * 4);            /* every try's hashes, for the tables */
   if (sharded)   /* merged ids (all rows), merged dists + results (own rows), exchanged lists */
     fixed += pad256(np * k * 4) + pad256(my_rows * k * w) + pad256(my_rows * k * 4) + pad256(my_rows * k * w) +
              pad256(T * my_rows * k * 4) + pad256(T * my_rows * k * w) +
@@ -451,6 +451,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   ftype *dout_dist = annh_arena_take(out_cap * k * w);
   void *dscratch = annh_arena_take(scratch_bytes);
   int *dstatus = annh_arena_take(sizeof(int));
+  annb_u32 *dhash_all = (sharded && save) ? annh_arena_take(T * n * 4) : NULL;
   annb_u32 *ds_ids = sharded ? annh_arena_take(T * my_rows * k * 4) : NULL;   /* [T][my_rows][k] */
   ftype *ds_dist = sharded ? annh_arena_take(T * my_rows * k * w) : NULL;
   CK(cudaMemsetAsync(dstatus, 0, sizeof(int), st));
@@ -514,7 +515,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
       const annb_u32 *hash_t = dhash + (j0 + j) * n;
       sp = span_begin(3);
       annb_build_buckets(hash_t, n, buckets, dcount, doffset, dorder_tmp, dorder, dtmax + t, dscan, st);
-      if (save) {                                  /* padded table for save->which_par[t] */
+      if (save && !sharded) {                      /* padded table for save->which_par[t] */
         annb_u32 tm = 0;
         CK(cudaMemcpyAsync(&tm, dtmax + t, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -593,6 +594,29 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
     }
   }
 
+  if (sharded && save) {
+    /* every rank gets every try's hashes, rebuilds the bucket tables and exports them     */
+    for (size_t j = 0; j < Tl; j++)
+      CK(cudaMemcpyAsync(dhash_all + own[j] * n, dhash + j * n, n * 4, cudaMemcpyDeviceToDevice, st));
+    for (size_t t = 0; t < T; t++)
+      annh_dist_broadcast(dhash_all + t * n, n * 4, annb200_dist_try_owner((int)t, R), st);
+    for (size_t t = 0; t < T; t++) {
+      annb_build_buckets(dhash_all + t * n, n, buckets, dcount, doffset, dorder_tmp, dorder, dtmax + t, dscan, st);
+      annb_u32 tm = 0;
+      CK(cudaMemcpyAsync(&tm, dtmax + t, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      size_t cells = buckets * (size_t)tm;
+      if (cells > G.table_cap) {
+        if (G.table_buf) CK(cudaFree(G.table_buf));
+        G.table_cap = cells + cells / 2 + 1024;
+        CK(cudaMalloc((void **)&G.table_buf, G.table_cap * sizeof(size_t)));
+      }
+      annb_export_table(doffset, dorder, n, buckets, tm, G.table_buf, st);
+      save->par_maxes[t] = tm;
+      save->which_par[t] = malloc((cells ? cells : 1) * sizeof(size_t));
+      CK(cudaMemcpyAsync(save->which_par[t], G.table_buf, cells * sizeof(size_t), cudaMemcpyDeviceToHost, st));
+    }
+  }
   HP("supercharge enqueued");
   /* 8. results: the egress threads are already widening the first chunks                 */
   annb_u32 *h_tmax = malloc(4 * T);

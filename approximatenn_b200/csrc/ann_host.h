@@ -50,6 +50,7 @@ int annh_dist_world(void);
 int annh_dist_gather_results(void);
 size_t annh_dist_padded_rows(size_t n);      /* capacity (rows) of arrays that get all-gathered */
 void annh_dist_allgather_rows(void *base, size_t n, size_t row_bytes, void *stream);
+void annh_dist_broadcast(void *buf, size_t bytes, int root, void *stream);
 void annh_dist_exchange_lists(const void *local, void *slice, size_t n, size_t row_bytes, int tries,
                               void *stream);
 

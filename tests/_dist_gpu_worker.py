@@ -35,6 +35,28 @@ def run_case(gpu, dtype, n, d, k, tries, seed, gather):
     return ok
 
 
+def run_save_case(gpu, dtype, n, d, k, tries, seed):
+    """save != NULL in sharded mode: every rank ends up with the complete index."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rng = np.random.default_rng(seed)
+    pts = rng.standard_normal((n, d)).astype(dtype)
+    y = rng.standard_normal((50, d)).astype(dtype)
+    orc = oracle.restatement(dtype)
+    want = orc.precomp(pts, k, tries, want_save=True, seed=seed)
+    got = gpu.precomp(pts, k, tries, want_save=True, seed=seed)
+    ok = np.array_equal(got.ids, want.ids) and np.array_equal(got.save.graph, want.save.graph)
+    ok &= np.array_equal(got.save.par_maxes, want.save.par_maxes)
+    ok &= np.array_equal(got.save.bases.view(np.uint8), want.save.bases.view(np.uint8))
+    ok &= np.array_equal(got.save.row_means.view(np.uint8), want.save.row_means.view(np.uint8))
+    for t in range(tries):
+        ok &= np.array_equal(got.save.which_par(t), want.save.which_par(t))
+    qa, qb = gpu.query(got.save, pts, y), orc.query(want.save, pts, y)
+    ok &= np.array_equal(qa.ids, qb.ids)
+    got.save.free(); want.save.free()
+    print(f"rank {rank}/{world} {np.dtype(dtype).name} n={n} save+query {'OK' if ok else 'MISMATCH'}", flush=True)
+    return ok
+
+
 def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -54,6 +76,8 @@ def main():
     ]
     for dtype, n, d, k, tries, seed, gather in cases:
         ok &= run_case(gpus[dtype], dtype, n, d, k, tries, seed, gather)
+    ok &= run_save_case(gpus[np.float32], np.float32, 6000, 32, 16, 5, 405)
+    ok &= run_save_case(gpus[np.float64], np.float64, 3000, 20, 10, 4, 406)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     for g in gpus.values():
