@@ -37,8 +37,7 @@ typedef struct {
   uint64_t fingerprint;
   ftype *d_points, *d_mean, *d_bases;
   annb_u32 *d_graph;
-  annb_u32 **d_tab;            /* host array of device pointers */
-  annb_u32 **d_tab_dev;        /* the same array on the device  */
+  annb_u32 **d_tab;            /* host array of device pointers to the 32-bit tables */
 } device_index;
 
 static device_index IDX;
@@ -73,7 +72,6 @@ static void drop_index(void) {
   CK(cudaFree(IDX.d_points)); CK(cudaFree(IDX.d_mean)); CK(cudaFree(IDX.d_bases));
   CK(cudaFree(IDX.d_graph));
   for (size_t t = 0; t < IDX.tries; t++) CK(cudaFree(IDX.d_tab[t]));
-  CK(cudaFree(IDX.d_tab_dev));
   free(IDX.d_tab);
   memset(&IDX, 0, sizeof IDX);
 }
@@ -112,8 +110,6 @@ static void build_index(const save_t *s, const ftype *points, uint64_t fp) {
   CK(cudaMemcpyAsync(IDX.d_bases, s->bases, T * s->d_short * s->d_long * w, cudaMemcpyHostToDevice, st));
   upload_narrow(s->graph, s->n * s->k, IDX.d_graph, tmp, st);
   for (size_t t = 0; t < T; t++) upload_narrow(s->which_par[t], B * s->par_maxes[t], IDX.d_tab[t], tmp, st);
-  CK(cudaMalloc((void **)&IDX.d_tab_dev, T * sizeof(annb_u32 *)));
-  CK(cudaMemcpyAsync(IDX.d_tab_dev, IDX.d_tab, T * sizeof(annb_u32 *), cudaMemcpyHostToDevice, st));
   CK(cudaStreamSynchronize(st));
   CK(cudaFree(tmp));
   IDX.live = 1;
