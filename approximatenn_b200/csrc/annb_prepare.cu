@@ -79,9 +79,9 @@ hash_points_kernel(const FT *__restrict__ points, const FT *__restrict__ mean,
     for (int tr = 0; tr < t.tries; tr++) {
       __syncthreads();
       // coalesced load of the tile, centred (compute.cl:44-49), stored transposed
-      for (size_t e = tid; e < rows * d; e += TP) {
-        size_t r = e / d, c = e - r * d;
-        V[c * LD + r] = points[p0 * d + e] - mean[c];
+      for (size_t r = tid >> 5; r < rows; r += TP / 32) {
+        const FT *src = points + (p0 + r) * d;
+        for (size_t c = tid & 31; c < d; c += 32) V[c * LD + r] = src[c] - mean[c];
       }
       __syncthreads();
       if ((size_t)tid < rows) {
@@ -168,9 +168,11 @@ hash_points_reg_kernel(const FT *__restrict__ points, const FT *__restrict__ mea
     const size_t p0 = tile * TP;
     const size_t rows = (t.n - p0 < (size_t)TP) ? t.n - p0 : (size_t)TP;
     __syncthreads();
-    for (size_t e = tid; e < rows * d; e += TP) {
-      size_t r = e / d, c = e - r * d;
-      V0[c * LD + r] = points[p0 * d + e] - mean[c];            // compute.cl:44-49
+    // rows are handed to warps, a warp reads a row with coalesced 128-byte requests; consecutive
+    // coordinates land in consecutive banks of the transposed tile (LD is odd)
+    for (size_t r = tid >> 5; r < rows; r += TP / 32) {
+      const FT *src = points + (p0 + r) * (size_t)d;
+      for (int c = tid & 31; c < d; c += 32) V0[c * LD + r] = src[c] - mean[c];   // compute.cl:44-49
     }
     __syncthreads();
     if ((size_t)tid >= rows) continue;
