@@ -474,8 +474,18 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   /* 4. S0 column means (alg.c:367-368); the accumulator borrows the sorted-copy buffer */
   span_end(sp);
   sp = span_begin(1);
-  annb_fold_rows(dX, dXs, n, d, 1, st);
-  for (size_t len = n >> 1; len >> 1; len >>= 1) annb_fold_rows(dXs, dXs, len, d, 0, st);
+  {
+    int left = floor_log2_sz(n);                   /* halvings until one row remains        */
+    size_t len = n;
+    const ftype *src = dX;
+    while (left > 0) {
+      int f = left < 4 ? left : 4;
+      annb_fold_rows(src, dXs, len, d, f, src == dX, st);
+      len >>= f;
+      left -= f;
+      src = dXs;
+    }
+  }
   annb_scale_means(dXs, n, d, dmean, st);
 
   /* 5. S1 hashes of every owned try in one pass over the points                         */

@@ -19,13 +19,37 @@ extern "C" void annb_literal_rows(unsigned long long out[3], int reset) {
 // S0: column means
 // =====================================================================================
 
-__global__ void fold_rows_kernel(const FT *__restrict__ src, FT *dst, size_t half, size_t len,
-                                 size_t d, int first) {
+// F levels of the reference's stride-halving row sum in one pass (alg.c:122-128):
+//   V_{i+1}[x] = V_i[x] + (V_i[x + len_{i+1}] + extra),  len_{i+1} = len_i / 2,
+//   extra = V_i[len_i - 1] for x == 0 when len_i is odd, else 0
+// (the very first level, on the raw points, associates as (a + b) + extra, compute.cl:19-20).
+// Fold<F>::get is the value of level +F at row x, evaluated as a compile-time recursion over the
+// 2^F (plus the rare odd-length extras) source rows it depends on — same additions, same order.
+template <int F>
+struct Fold {
+  static __device__ __forceinline__ FT get(const FT *__restrict__ src, size_t len, size_t d, size_t x,
+                                           size_t c, bool first) {
+    const size_t lp = len >> (F - 1), h = lp >> 1;
+    FT a = Fold<F - 1>::get(src, len, d, x, c, first);
+    FT b = Fold<F - 1>::get(src, len, d, x + h, c, first);
+    FT e = (x == 0 && (lp & 1)) ? Fold<F - 1>::get(src, len, d, lp - 1, c, first) : (FT)0;
+    return (F == 1 && first) ? (a + b) + e : a + (b + e);
+  }
+};
+template <>
+struct Fold<0> {
+  static __device__ __forceinline__ FT get(const FT *__restrict__ src, size_t, size_t d, size_t x, size_t c, bool) {
+    return src[x * d + c];
+  }
+};
+
+template <int F>
+__global__ void fold_rows_kernel(const FT *src, FT *dst, size_t len, size_t d, int first) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= half * d) return;
-  FT a = src[e], b = src[e + half * d];
-  FT extra = (e < d && (len & 1)) ? src[(len - 1) * d + e] : (FT)0;
-  dst[e] = first ? (a + b) + extra : a + (b + extra);
+  const size_t out_rows = len >> F;
+  if (e >= out_rows * d) return;
+  size_t x = e / d, c = e - x * d;
+  dst[e] = Fold<F>::get(src, len, d, x, c, first != 0);
 }
 
 __global__ void scale_means_kernel(const FT *acc, size_t n, size_t d, FT *mean) {
@@ -33,11 +57,18 @@ __global__ void scale_means_kernel(const FT *acc, size_t n, size_t d, FT *mean) 
   if (c < d) mean[c] = acc[c] / (FT)n;
 }
 
-extern "C" void annb_fold_rows(const FT *src, FT *dst, size_t len, size_t d, int first,
+extern "C" void annb_fold_rows(const FT *src, FT *dst, size_t len, size_t d, int levels, int first,
                                annb_stream stream) {
-  size_t half = len / 2;
-  if (half == 0) return;
-  fold_rows_kernel<<<grid_for(half * d, 256), 256, 0, stream>>>(src, dst, half, len, d, first);
+  size_t out = (len >> levels) * d;
+  if (out == 0) return;
+  unsigned grid = grid_for(out, 256);
+  switch (levels) {
+    case 1: fold_rows_kernel<1><<<grid, 256, 0, stream>>>(src, dst, len, d, first); break;
+    case 2: fold_rows_kernel<2><<<grid, 256, 0, stream>>>(src, dst, len, d, first); break;
+    case 3: fold_rows_kernel<3><<<grid, 256, 0, stream>>>(src, dst, len, d, first); break;
+    case 4: fold_rows_kernel<4><<<grid, 256, 0, stream>>>(src, dst, len, d, first); break;
+    default: fatal_config("annb_fold_rows: 1..4 levels per pass");
+  }
   LAUNCH_CHECK("fold_rows");
 }
 

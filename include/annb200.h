@@ -24,11 +24,13 @@ typedef unsigned int annb_u32;
 typedef struct CUstream_st *annb_stream;      /* == cudaStream_t */
 
 /* ---- S0: column means --------------------------------------------------------------
- * One level of the reference's stride-halving row sum (alg.c:122-128;
- * compute.cl:15-31): dst[x][c] = src[x][c] + src[x+len/2][c] (+ src[len-1][c] for x == 0 when
- * len is odd), x < len/2, with the reference's association order for the first level
- * (first != 0) and for the in-place levels (first == 0).  dst may alias src when first == 0. */
-void annb_fold_rows(const ftype *src, ftype *dst, size_t len, size_t d, int first,
+ * `levels` (1..4) levels of the reference's stride-halving row sum in one pass (alg.c:122-128;
+ * compute.cl:15-31): each level maps rows [0,len) to rows [0,len/2) as
+ * dst[x][c] = src[x][c] + src[x+len/2][c] (+ src[len-1][c] for x == 0 when len is odd), with the
+ * reference's association order for the first level on the raw points (first != 0) and for
+ * the in-place levels.  Writes (len >> levels) rows; dst may alias src when first == 0.
+ * Needs len >> (levels-1) >= 2.                                                             */
+void annb_fold_rows(const ftype *src, ftype *dst, size_t len, size_t d, int levels, int first,
                     annb_stream stream);
 /* mean[c] = acc[c] / n   (compute.cl:36-39) */
 void annb_scale_means(const ftype *acc, size_t n, size_t d, ftype *mean, annb_stream stream);
