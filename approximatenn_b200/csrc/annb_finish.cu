@@ -126,18 +126,17 @@ merge_lists_fast_kernel(const u32 *__restrict__ lists_ids, const FT *__restrict_
     u32 ni = nxt_i;
     nxt_v = nxt_v2; nxt_i = nxt_i2;
     fetch(li + 2, nxt_v2, nxt_i2);
-    if (__ballot_sync(FULL, mine && src < admit && nv == ft_inf())) any_inf = true;
-    {
-      // largest finite admitted entry of this list (prefix-corner rule)
-      FT cv = (mine && nv != ft_inf()) ? nv : -ft_inf();
-      u32 ci = ni;
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        FT ov = __shfl_xor_sync(FULL, cv, o);
-        u32 oi = __shfl_xor_sync(FULL, ci, o);
-        if (ov > cv) { cv = ov; ci = oi; }
+    if (a.corner_list >= 0) {                      // bookkeeping of the prefix-corner rule only
+      if (__ballot_sync(FULL, mine && src < admit && nv == ft_inf())) any_inf = true;
+      // the list is sorted, so its largest finite admitted entry is the last finite one:
+      // highest such lane for the ascending list 0, lowest for the descending ones
+      unsigned fin = __ballot_sync(FULL, mine && src < admit && nv != ft_inf());
+      if (fin) {
+        int at = li == 0 ? 31 - __clz(fin) : __ffs(fin) - 1;
+        FT cv = __shfl_sync(FULL, nv, at);
+        u32 ci = __shfl_sync(FULL, ni, at);
+        if (cv > max_v) { max_v = cv; max_id = ci; }
       }
-      if (cv > max_v) { max_v = cv; max_id = ci; }
     }
     if (mine) { v = nv; id = ni; }
     if (li == 0) {
