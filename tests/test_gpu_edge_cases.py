@@ -102,3 +102,19 @@ def test_invalid_arguments_are_fatal_like_the_reference(k, tries, rb, lb, needle
     out = subprocess.run([sys.executable, "-c", BAD % (k, tries, rb, lb)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 1 and "COMPUTED" not in out.stdout
     assert needle in out.stderr, out.stderr
+
+
+def test_cleanup_then_reuse(gpu, oracle_mod):
+    """gpu_cleanup() releases every device and pinned allocation; the next call re-initialises
+    (the reference's programs call gpu_init()/gpu_cleanup() around their loops)."""
+    rng = np.random.default_rng(12)
+    pts = rng.standard_normal((3000, 32)).astype(np.float32)
+    b = gpu[np.dtype(np.float32)]
+    want = oracle_mod.restatement(np.float32).precomp(pts, 16, 4, seed=3)
+    for _ in range(2):
+        got = b.precomp(pts, 16, 4, want_save=True, seed=3)
+        q = b.query(got.save, pts, pts[:10])
+        assert np.array_equal(got.ids, want.ids) and same_bits(got.dists, want.dists)
+        got.save.free()
+        b.lib.gpu_cleanup()
+    b.lib.gpu_init()
