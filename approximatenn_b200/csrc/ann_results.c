@@ -36,6 +36,7 @@
 #define EGRESS_MAX_THREADS 16
 
 typedef struct { size_t r0, r1; cudaEvent_t done; } egress_chunk;
+typedef struct { struct annh_egress *e; int idx; } egress_arg;
 
 struct annh_egress {
   size_t rows, k;
@@ -45,7 +46,7 @@ struct annh_egress {
   ftype *stage_dist;
   int device, nthreads;
   pthread_t th[EGRESS_MAX_THREADS];
-  struct { struct annh_egress *e; int idx; } arg[EGRESS_MAX_THREADS];
+  egress_arg arg[EGRESS_MAX_THREADS];
   pthread_mutex_t mu;
   pthread_cond_t cv;
   int submitted, closed;
@@ -72,8 +73,8 @@ void annh_egress_release(void) {
 }
 
 static void *egress_worker(void *p) {
-  struct annh_egress *e = ((struct { struct annh_egress *e; int idx; } *)p)->e;
-  const int me = ((struct { struct annh_egress *e; int idx; } *)p)->idx;
+  struct annh_egress *e = ((egress_arg *)p)->e;
+  const int me = ((egress_arg *)p)->idx;
   cudaSetDevice(e->device);
   /* 1. fault in this thread's share of the result pages while the GPU computes          */
   {

@@ -27,6 +27,16 @@ void annb_finish_literal_counts(unsigned long long out[2], int reset);
     }                                                                                   \
   } while (0)
 
+// runtime calls made by the launch layer itself (memsets, attribute changes): fatal like launches
+#define RT_CHECK(call)                                                                  \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      fprintf(stderr, "approximatenn_b200: %s failed: %s\n", #call, cudaGetErrorString(e_)); \
+      exit(1);                                                                          \
+    }                                                                                   \
+  } while (0)
+
 static inline void fatal_config(const char *what) {
   fprintf(stderr, "approximatenn_b200: unsupported configuration: %s\n", what);
   exit(1);
@@ -337,17 +347,4 @@ __device__ __forceinline__ void block_row_distances(const FT *__restrict__ qrow,
       if (lane == 0) emit(i, dist);
     }
   }
-}
-
-// exact squared distance between two global rows, result warp-uniform; E as in row_mode()
-template <int E>
-__device__ __forceinline__ FT row_sqdist(const FT *__restrict__ a, const FT *__restrict__ b, int d,
-                                         FT *tmp, int lane) {
-  if (E) {
-    WarpRow<(E ? E : 1)> ra, rb;
-    ra.load(a, lane, d);
-    rb.load(b, lane, d);
-    return __shfl_sync(FULL, warp_sqdist<(E ? E : 1)>(ra, rb, d), 0);
-  }
-  return generic_sqdist(a, b, d, tmp, lane);
 }

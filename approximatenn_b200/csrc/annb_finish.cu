@@ -247,7 +247,7 @@ extern "C" void annb_merge_lists(const u32 *lists_ids, const FT *lists_dist, int
   for (int i = 0; i < n_lists; i++) a.admit[i] = host_admit[i];
   a.corner_list = corner_list;
   a.corner_pos = corner_pos;
-  if (whole_row) cudaMemsetAsync(ls.list.count, 0, sizeof(u32), stream);
+  if (whole_row) RT_CHECK(cudaMemsetAsync(ls.list.count, 0, sizeof(u32), stream));
   TieList f = whole_row ? ls.list : all_rows;        // rows == NULL: ties are not recorded
   dim3 block(256), grid(grid_for(n * 32, 256));
   const char *nofast = getenv("ANN_B200_NO_FAST_MERGE");
@@ -597,7 +597,7 @@ static void launch_supercharge(int regs, size_t smem, annb_stream stream, const 
 #define SC_CASE(R)                                                                               \
   {                                                                                              \
     if (smem > 48 * 1024)                                                                        \
-      cudaFuncSetAttribute(supercharge_kernel<E, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      RT_CHECK(cudaFuncSetAttribute(supercharge_kernel<E, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     supercharge_kernel<E, R><<<grid, block, smem, stream>>>(queries, points, own_ids, own_dist, graph, n, d, k, rb, re, ex, out_ids, out_dist, ls.list); \
   }
   if (!all_literal && !skip_main) {
@@ -611,7 +611,7 @@ static void launch_supercharge(int regs, size_t smem, annb_stream stream, const 
   }
 #undef SC_CASE
   if (smem > 48 * 1024)
-    cudaFuncSetAttribute(supercharge_literal_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RT_CHECK(cudaFuncSetAttribute(supercharge_literal_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   TieList which = ls.list;
   if (all_literal) which.rows = NULL;
   supercharge_literal_kernel<E><<<all_literal ? 148 * 4 : 148 * 2, 256, smem, stream>>>(
@@ -635,7 +635,7 @@ extern "C" void annb_supercharge(const FT *queries, const FT *points, const u32 
   LiteralScratch ls = carve_literal_scratch(scratch, scratch_bytes, rows);
   const bool all_literal = k * (k + 1) < 16;      // the network degenerates: literal rows only
   bool all_literal_redo_only = false;             // fast kernel already ran: only the reported redo
-  cudaMemsetAsync(ls.list.count, 0, sizeof(u32), stream);
+  RT_CHECK(cudaMemsetAsync(ls.list.count, 0, sizeof(u32), stream));
   // fast path
   {
     const char *off = getenv("ANN_B200_NO_FAST_SUPERCHARGE");
@@ -647,7 +647,7 @@ extern "C" void annb_supercharge(const FT *queries, const FT *points, const u32 
 #define FAST_CASE(EE)                                                                              \
   {                                                                                                \
     if (fsmem > 48 * 1024)                                                                         \
-      cudaFuncSetAttribute(supercharge_fast_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem); \
+      RT_CHECK(cudaFuncSetAttribute(supercharge_fast_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); \
     supercharge_fast_kernel<EE><<<grid, block, fsmem, stream>>>(queries, points, own_ids, own_dist, graph, n, (int)k, row_begin, row_end, exclude_self, out_ids, out_dist, ls.list); \
   }
       switch (epl) {

@@ -580,7 +580,7 @@ static void launch_warp_r(int regs, dim3 grid, dim3 block, size_t smem, annb_str
 #define WARP_CASE(R)                                                                             \
   {                                                                                              \
     if (smem > 48 * 1024)                                                                        \
-      cudaFuncSetAttribute(leaf_topk_warp_kernel<E, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      RT_CHECK(cudaFuncSetAttribute(leaf_topk_warp_kernel<E, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     leaf_topk_warp_kernel<E, R><<<grid, block, smem, stream>>>(sp, order, offset, hash, tmax, n, d, d_short, k, ids, dist, flags); \
   }
   switch (regs) {
@@ -599,7 +599,7 @@ static void launch_tile(annb_stream stream, const FT *sp, const u32 *order, cons
   size_t smem = TileSmem<D, KC, B>::per_warp * TILE_WARPS;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(leaf_topk_tile_kernel<D, KC, B, REGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RT_CHECK(cudaFuncSetAttribute(leaf_topk_tile_kernel<D, KC, B, REGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   unsigned grid = (unsigned)((buckets + TILE_WARPS - 1) / TILE_WARPS);
@@ -611,7 +611,7 @@ static void launch_tile(annb_stream stream, const FT *sp, const u32 *order, cons
     if (grid > resident) grid = resident;
   }
   u32 *ticket = flags.count + 32;                           // spare words of the tie-list header
-  cudaMemsetAsync(ticket, 0, sizeof(u32), stream);
+  RT_CHECK(cudaMemsetAsync(ticket, 0, sizeof(u32), stream));
   static int pack_tries = -1, max_slices = 16;
   if (pack_tries < 0) {
     const char *e1 = getenv("ANN_B200_TILE_PASSES"), *e2 = getenv("ANN_B200_TILE_SLICES");
@@ -664,7 +664,7 @@ extern "C" void annb_leaf_topk(const FT *sorted_points, const u32 *order, const 
   TieList flags = ls.list;
   unsigned char *slabs = ls.slabs;
   size_t slab_bytes = ls.slab_bytes;
-  cudaMemsetAsync(flags.count, 0, sizeof(u32), stream);
+  RT_CHECK(cudaMemsetAsync(flags.count, 0, sizeof(u32), stream));
   const size_t buckets = (size_t)1 << d_short;
   int mode = row_mode(d);
   size_t gsmem = mode ? 0 : 8 * d * sizeof(FT);
@@ -692,7 +692,7 @@ extern "C" void annb_leaf_topk(const FT *sorted_points, const u32 *order, const 
 #define L_CASE(EE)                                                                                \
   {                                                                                               \
     if (gsmem > 48 * 1024)                                                                        \
-      cudaFuncSetAttribute(leaf_literal_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem); \
+      RT_CHECK(cudaFuncSetAttribute(leaf_literal_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem)); \
     leaf_literal_kernel<EE><<<lgrid, lblock, gsmem, stream>>>(L_ARGS);                            \
   }
   switch (mode) {

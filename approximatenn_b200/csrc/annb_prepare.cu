@@ -264,7 +264,7 @@ static bool launch_hash_reg(const FT *points, const FT *mean, const annb_transfo
   if (smem > 200 * 1024) return false;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(hash_points_reg_kernel<DM, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    RT_CHECK(cudaFuncSetAttribute(hash_points_reg_kernel<DM, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
   size_t tiles = (t->n + TP - 1) / TP;
@@ -309,8 +309,8 @@ extern "C" void annb_hash_points(const FT *points, const FT *mean, const annb_tr
   if (need <= HASH_SMEM_LIMIT) {
     static size_t configured = 0;
     if (need > configured) {
-      cudaFuncSetAttribute(hash_points_kernel<HASH_TP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)HASH_SMEM_LIMIT);
+      RT_CHECK(cudaFuncSetAttribute(hash_points_kernel<HASH_TP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)HASH_SMEM_LIMIT));
       configured = HASH_SMEM_LIMIT;
     }
     unsigned grid = (unsigned)(tiles < 148 * 16 ? tiles : 148 * 16);
@@ -458,8 +458,8 @@ extern "C" void annb_build_buckets(const u32 *hash, size_t n, size_t buckets, u3
                                    void *scan_tmp, annb_stream stream) {
   u32 *block_tot = (u32 *)scan_tmp;
   size_t blocks = (buckets + SCAN_ITEMS - 1) / SCAN_ITEMS;
-  cudaMemsetAsync(count, 0, buckets * sizeof(u32), stream);
-  cudaMemsetAsync(tmax, 0, sizeof(u32), stream);
+  RT_CHECK(cudaMemsetAsync(count, 0, buckets * sizeof(u32), stream));
+  RT_CHECK(cudaMemsetAsync(tmax, 0, sizeof(u32), stream));
   histogram_kernel<<<grid_for(n, 256), 256, 0, stream>>>(hash, n, count);
   LAUNCH_CHECK("histogram");
   scan_blocks_kernel<<<(unsigned)blocks, SCAN_THREADS, 0, stream>>>(count, buckets, offset, block_tot, tmax);

@@ -59,7 +59,7 @@ extern "C" void annb_query_hash(const FT *y, const FT *mean, const FT *bases, si
   size_t smem = 8 * d * sizeof(FT);
   if (smem > 200 * 1024) fatal_config("d too large for the query projection");
   if (smem > 48 * 1024)
-    cudaFuncSetAttribute(query_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RT_CHECK(cudaFuncSetAttribute(query_hash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   query_hash_kernel<<<grid_for(ycnt * tries * 32, 256), 256, smem, stream>>>(y, mean, bases, ycnt, (int)d, (int)d_short, tries, sign);
   LAUNCH_CHECK("query_hash");
 }
@@ -211,7 +211,7 @@ static void launch_query_rows(int regs, size_t smem, annb_stream stream, const F
 #define QR_CASE(R)                                                                                \
   {                                                                                               \
     if (smem > 48 * 1024)                                                                         \
-      cudaFuncSetAttribute(query_rows_kernel<E, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      RT_CHECK(cudaFuncSetAttribute(query_rows_kernel<E, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     query_rows_kernel<E, R><<<grid, block, smem, stream>>>(y, points, q, sign, n, ycnt, d, d_short, k, ex, ids, dist, ls.list); \
   }
   switch (regs) {
@@ -223,7 +223,7 @@ static void launch_query_rows(int regs, size_t smem, annb_stream stream, const F
 #undef QR_CASE
   LAUNCH_CHECK("query_rows");
   if (smem > 48 * 1024)
-    cudaFuncSetAttribute(query_literal_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RT_CHECK(cudaFuncSetAttribute(query_literal_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   query_literal_kernel<E><<<148 * 2, 256, smem, stream>>>(y, points, q, sign, n, ycnt, d, d_short, k, ex, ids, dist, ls.list, ls.slabs, ls.slab_bytes, status);
   LAUNCH_CHECK("query_literal");
 }
@@ -252,7 +252,7 @@ extern "C" void annb_query_rows(const FT *y, const FT *points, const u32 *const 
   size_t smem = mode ? 0 : 8 * d * sizeof(FT);
   if (smem > 200 * 1024) fatal_config("d too large for the generic distance path");
   LiteralScratch ls = carve_literal_scratch(scratch, scratch_bytes, ycnt);
-  cudaMemsetAsync(ls.list.count, 0, sizeof(u32), stream);
+  RT_CHECK(cudaMemsetAsync(ls.list.count, 0, sizeof(u32), stream));
 #define Q_ARGS regs, smem, stream, y, points, q, sign, n, ycnt, (int)d, (int)d_short, (int)k, exclude_self, list_ids, list_dist, ls, status
   switch (mode) {
     case 0: launch_query_rows<0>(Q_ARGS); break;
