@@ -360,7 +360,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   if (sharded && T > 64) annh_fatal("%s", "more than 64 tries in sharded mode");
   const int full_result = !sharded || annh_dist_gather_results() || save != NULL;
   const size_t out_rows = full_result ? n : my_rows;
-  annh_egress *eg = annh_egress_begin(out_rows, k, dists_o != NULL, G.device);
+  annh_egress *eg = annh_egress_begin(out_rows, k, dists_o != NULL, save != NULL, G.device);
 
   HP("egress_begin");
   /* 1. transforms: ALL tries are drawn before any compute (alg.c:388-392), on every rank   */
@@ -539,6 +539,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
         annb_export_table(doffset, dorder, n, buckets, tm, dtable, st);
         save->par_maxes[t] = tm;
         save->which_par[t] = malloc((cells ? cells : 1) * sizeof(size_t));
+        annh_prefault(save->which_par[t], cells * sizeof(size_t));
         CK(cudaMemcpyAsync(save->which_par[t], dtable, cells * sizeof(size_t), cudaMemcpyDeviceToHost, st));
       }
       annb_gather_rows(dX, dorder, n, d, dXs, st);
@@ -624,6 +625,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
       annb_export_table(doffset, dorder, n, buckets, tm, G.table_buf, st);
       save->par_maxes[t] = tm;
       save->which_par[t] = malloc((cells ? cells : 1) * sizeof(size_t));
+      annh_prefault(save->which_par[t], cells * sizeof(size_t));
       CK(cudaMemcpyAsync(save->which_par[t], G.table_buf, cells * sizeof(size_t), cudaMemcpyDeviceToHost, st));
     }
   }
@@ -636,7 +638,8 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   CK(cudaStreamSynchronize(st));
   HP("stream drained");
   collect_times();
-  size_t *result = annh_egress_end(eg, dists_o);
+  size_t *graph_copy = NULL;
+  size_t *result = annh_egress_end(eg, dists_o, &graph_copy);
   HP("egress_end");
   if (h_status) annh_fatal("%s", "scratch too small for a literal candidate row (extremely unbalanced buckets)");
   for (size_t j = 0; j < Tl; j++)
@@ -644,11 +647,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
       annh_fatal("%s", "candidate rows shorter than 16 slots (n far too small for this k)");
   free(h_tmax);
 
-  if (save) {                                                   /* alg.c:428-432 */
-    save->graph = result;
-    result = malloc(sizeof(size_t) * n * k);
-    memcpy(result, save->graph, sizeof(size_t) * n * k);
-  }
+  if (save) save->graph = graph_copy;                           /* alg.c:428-432: two separate copies */
   for (size_t t = 0; t < T; t++) free_transform(tf + t);
   free(tf); free(own); free(h_idx); free(h_cs); free(h_permb); free(h_pick);
   return result;

@@ -37,11 +37,12 @@ void annh_set_timing(int on);
 /* result egress (ann_results.c): malloc()ed result arrays filled chunk by chunk through a
  * pinned staging buffer while later chunks are still being computed                        */
 typedef struct annh_egress annh_egress;
-annh_egress *annh_egress_begin(size_t rows, size_t k, int want_dist, int device);
+annh_egress *annh_egress_begin(size_t rows, size_t k, int want_dist, int want_second_ids, int device);
 int annh_egress_chunks(const annh_egress *e);          /* how many row chunks to produce    */
 void annh_egress_chunk(annh_egress *e, size_t r0, size_t r1, const void *dev_ids_u32,
                        const void *dev_dist, void *producer_stream);
-size_t *annh_egress_end(annh_egress *e, ftype **dists_o);
+size_t *annh_egress_end(annh_egress *e, ftype **dists_o, size_t **second_ids_o);
+void annh_prefault(void *ptr, size_t bytes);   /* touch the pages of a fresh allocation, 4 threads */
 void annh_egress_release(void);
 
 /* sharded execution (ann_dist.c); world == 1 unless annb200_dist_init() was called          */

@@ -139,7 +139,7 @@ size_t *query_gpu(const save_t *save, const ftype *points, size_t ycnt, const ft
         IDX.fingerprint == fp))
     build_index(save, points, fp);
 
-  annh_egress *eg = annh_egress_begin(ycnt, k, dists_o != NULL, annh_device());
+  annh_egress *eg = annh_egress_begin(ycnt, k, dists_o != NULL, 0, annh_device());
   const size_t scratch_bytes = ycnt * 4 + 1024 + ((size_t)64 << 20);
   size_t need = (ycnt * d * w + 256) + (T * ycnt * 4 + 256) + 2 * (ycnt * k * 4 + 256) +
                 2 * (ycnt * k * w + 256) + scratch_bytes + 4096;
@@ -173,7 +173,7 @@ size_t *query_gpu(const save_t *save, const ftype *points, size_t ycnt, const ft
   int h_status = 0;
   CK(cudaMemcpyAsync(&h_status, dstatus, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  size_t *result = annh_egress_end(eg, dists_o);
+  size_t *result = annh_egress_end(eg, dists_o, NULL);
   if (h_status) annh_fatal("%s", "scratch too small for a literal candidate row");
   if (!use_cache) drop_index();
   return result;

@@ -41,6 +41,7 @@ typedef struct { struct annh_egress *e; int idx; } egress_arg;
 struct annh_egress {
   size_t rows, k;
   size_t *ids;            /* [rows][k] result, caller-owned after end()        */
+  size_t *ids2;           /* optional second copy (save->graph), same contents  */
   ftype *dist;            /* [rows][k] or NULL                                 */
   annb_u32 *stage_ids;    /* pinned staging (cached in S)                      */
   ftype *stage_dist;
@@ -83,6 +84,11 @@ static void *egress_worker(void *p) {
     volatile char *a = (volatile char *)(e->ids + lo);
     for (size_t o = 0; o < (hi - lo) * sizeof(size_t); o += 4096) a[o] = 0;
     if (hi > lo) a[(hi - lo) * sizeof(size_t) - 1] = 0;
+    if (e->ids2) {
+      volatile char *a2 = (volatile char *)(e->ids2 + lo);
+      for (size_t o = 0; o < (hi - lo) * sizeof(size_t); o += 4096) a2[o] = 0;
+      if (hi > lo) a2[(hi - lo) * sizeof(size_t) - 1] = 0;
+    }
     if (e->dist) {
       volatile char *b = (volatile char *)(e->dist + lo);
       for (size_t o = 0; o < (hi - lo) * sizeof(ftype); o += 4096) b[o] = 0;
@@ -107,18 +113,24 @@ static void *egress_worker(void *p) {
     size_t hi = (ch->r0 + rows * (size_t)(me + 1) / e->nthreads) * e->k;
     const annb_u32 *src = e->stage_ids;
     size_t *dst = e->ids;
-    for (size_t i = lo; i < hi; i++) dst[i] = src[i];
+    if (e->ids2) {
+      size_t *dst2 = e->ids2;
+      for (size_t i = lo; i < hi; i++) dst[i] = dst2[i] = src[i];
+    } else {
+      for (size_t i = lo; i < hi; i++) dst[i] = src[i];
+    }
     if (e->dist) memcpy(e->dist + lo, e->stage_dist + lo, (hi - lo) * sizeof(ftype));
   }
   return NULL;
 }
 
-annh_egress *annh_egress_begin(size_t rows, size_t k, int want_dist, int device) {
+annh_egress *annh_egress_begin(size_t rows, size_t k, int want_dist, int want_second_ids, int device) {
   annh_egress *e = calloc(1, sizeof *e);
   e->rows = rows; e->k = k; e->device = device;
   e->ids = malloc(sizeof(size_t) * rows * k);
   e->dist = want_dist ? malloc(sizeof(ftype) * rows * k) : NULL;
-  if (!e->ids || (want_dist && !e->dist)) annh_fatal("%s", "out of host memory for the result arrays");
+  e->ids2 = want_second_ids ? malloc(sizeof(size_t) * rows * k) : NULL;
+  if (!e->ids || (want_dist && !e->dist) || (want_second_ids && !e->ids2)) annh_fatal("%s", "out of host memory for the result arrays");
   if (!S.ready) {
     CK(cudaStreamCreateWithFlags(&S.copy, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&S.produced, cudaEventDisableTiming));
@@ -175,7 +187,7 @@ void annh_egress_chunk(annh_egress *e, size_t r0, size_t r1, const void *dev_ids
   pthread_mutex_unlock(&e->mu);
 }
 
-size_t *annh_egress_end(annh_egress *e, ftype **dists_o) {
+size_t *annh_egress_end(annh_egress *e, ftype **dists_o, size_t **second_ids_o) {
   pthread_mutex_lock(&e->mu);
   e->closed = 1;
   pthread_cond_broadcast(&e->cv);
@@ -186,6 +198,34 @@ size_t *annh_egress_end(annh_egress *e, ftype **dists_o) {
   pthread_cond_destroy(&e->cv);
   size_t *ids = e->ids;
   if (dists_o) *dists_o = e->dist;
+  if (second_ids_o) *second_ids_o = e->ids2;
   free(e);
   return ids;
+}
+
+/* Touches the pages of a freshly malloc()ed block with a few threads, so that a following
+ * device->host copy into it does not page-fault 4 KB at a time on one thread.              */
+typedef struct { volatile char *p; size_t bytes; } touch_job;
+static void *touch_main(void *a) {
+  touch_job *j = a;
+  for (size_t o = 0; o < j->bytes; o += 4096) j->p[o] = 0;
+  if (j->bytes) j->p[j->bytes - 1] = 0;
+  return NULL;
+}
+void annh_prefault(void *ptr, size_t bytes) {
+  enum { NT = 4 };
+  if (bytes < ((size_t)4 << 20)) return;
+  pthread_t th[NT];
+  touch_job job[NT];
+  size_t per = ((bytes / NT) + 4095) & ~(size_t)4095;
+  int started = 0;
+  for (int i = 0; i < NT; i++) {
+    size_t lo = per * (size_t)i;
+    if (lo >= bytes) break;
+    job[i].p = (volatile char *)ptr + lo;
+    job[i].bytes = bytes - lo < per ? bytes - lo : per;
+    if (pthread_create(&th[i], NULL, touch_main, &job[i]) != 0) break;
+    started++;
+  }
+  for (int i = 0; i < started; i++) pthread_join(th[i], NULL);
 }

@@ -169,6 +169,44 @@ def measure_recall(gpu, pts, cfg, sample):
             "against": "exact brute force (fp32) over all n points"}
 
 
+def measure_pair(gpu, pts, cfg, ycnt):
+    """The "precomp + query" pair of the metric: precomp WITH the save structure,
+    then query() of `ycnt` fresh Gaussian vectors against it — first call (uploads the index to
+    the device) and later calls (index resident).  Bare C-ABI calls with host buffers, result
+    arrays freed inside the timed spans like the reference's time_results does."""
+    from approximatenn_b200.api import SaveT, srandom, _libc
+    n, d, k, tries, dtype = cfg
+    rng = np.random.default_rng(11)
+    y = np.ascontiguousarray(rng.standard_normal((ycnt, d), dtype=np.float32).astype(dtype))
+    sv = SaveT()
+
+    def precomp_save():
+        dptr = ctypes.c_void_p()
+        srandom(1001)
+        t0 = time.perf_counter()
+        ids = gpu.precomp_raw(n, k, d, pts.ctypes.data, tries, *ROT, ctypes.byref(sv), ctypes.byref(dptr))
+        _libc.free(ids); _libc.free(dptr)
+        return time.perf_counter() - t0
+
+    def query():
+        dptr = ctypes.c_void_p()
+        t0 = time.perf_counter()
+        ids = gpu._query(ctypes.byref(sv), pts.ctypes.data, ycnt, y.ctypes.data, ctypes.byref(dptr))
+        _libc.free(ids); _libc.free(dptr)
+        return time.perf_counter() - t0
+
+    precomp_save()                       # warm: table staging buffer, arena
+    gpu._free_save(ctypes.byref(sv))
+    tp = precomp_save()
+    q1 = query()
+    q2 = min(query() for _ in range(3))
+    gpu._free_save(ctypes.byref(sv))
+    return {"precomp_with_save_ms": 1e3 * tp, "precomp_with_save_points_per_s": n / tp,
+            "query_count": ycnt, "query_first_call_ms": 1e3 * q1, "query_resident_index_ms": 1e3 * q2,
+            "queries_per_s_resident": ycnt / q2,
+            "pair_ms": 1e3 * (tp + q1), "pair_points_plus_queries_per_s": (n + ycnt) / (tp + q1)}
+
+
 def run_reference_arm(args, cfg, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -211,6 +249,8 @@ def main():
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--cpu-sample", type=int, default=256, help="points in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pair-queries", type=int, default=65536,
+                    help="query vectors of the precomp(save)+query pair measurement (0 = skip)")
     ap.add_argument("--recall-sample", type=int, default=2000,
                     help="points whose exact k nearest neighbours are brute-forced for recall@k (0 = skip)")
     args = ap.parse_args()
@@ -356,6 +396,8 @@ def main():
             "clocks": sampler.summary()}
     if args.recall_sample > 0 and world == 1:
         line["recall"] = measure_recall(gpu, pts, cfg, args.recall_sample)
+    if args.pair_queries > 0 and world == 1:
+        line["precomp_query_pair"] = measure_pair(gpu, pts, cfg, args.pair_queries)
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, pts, args.cpu_sample)
     sys.stdout.flush()
