@@ -494,6 +494,8 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   if (Tl) annb_hash_points(dX, dmean, &desc, dhash, dhscratch, st);
   span_end(sp);
 
+  int adopt = 0;
+  if (save && !sharded) adopt = annh_index_adopt_begin(n, k, d_short, d, T);
   if (save) {
     save->tries = tries; save->n = n; save->k = k; save->d_short = d_short; save->d_long = d;
     save->row_means = malloc(w * d);
@@ -537,6 +539,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
         }
         size_t *dtable = G.table_buf;
         annb_export_table(doffset, dorder, n, buckets, tm, dtable, st);
+        if (adopt) annh_index_adopt_table((int)t, dtable, cells);
         save->par_maxes[t] = tm;
         save->which_par[t] = malloc((cells ? cells : 1) * sizeof(size_t));
         annh_prefault(save->which_par[t], cells * sizeof(size_t));
@@ -648,6 +651,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   free(h_tmax);
 
   if (save) save->graph = graph_copy;                           /* alg.c:428-432: two separate copies */
+  if (adopt) annh_index_adopt_finish(save, points, dX, dmean, dout_ids);
   for (size_t t = 0; t < T; t++) free_transform(tf + t);
   free(tf); free(own); free(h_idx); free(h_cs); free(h_permb); free(h_pick);
   return result;

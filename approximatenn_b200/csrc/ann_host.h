@@ -3,6 +3,7 @@
 #define ANN_HOST_H
 #include <stddef.h>
 #include "ann.h"
+#include "annb200.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -59,6 +60,12 @@ void annh_dist_exchange_lists(const void *local, void *slice, size_t n, size_t r
  * host threads when the source is pageable                                                 */
 void annh_ingest(void *dst, const void *src, size_t bytes, void *consumer_stream, int device);
 void annh_ingest_release(void);
+
+/* precomp_gpu(save != NULL) hands its device-resident data to the query cache (ann_query.c) */
+int annh_index_adopt_begin(size_t n, size_t k, size_t d_short, size_t d, size_t tries);
+void annh_index_adopt_table(int t, const size_t *dev_table, size_t cells);
+void annh_index_adopt_finish(const save_t *s, const ftype *host_points, const ftype *dev_points,
+                             const ftype *dev_mean, const annb_u32 *dev_graph);
 
 /* drops any device-resident copy of `save` kept for query_gpu (called by free_save)      */
 void annh_forget_save(const save_t *save);

@@ -38,6 +38,9 @@ typedef struct {
   ftype *d_points, *d_mean, *d_bases;
   annb_u32 *d_graph;
   annb_u32 **d_tab;            /* host array of device pointers to the 32-bit tables */
+  /* capacities in bytes: the buffers are grow-only and survive a dropped index, because
+   * cudaMalloc/cudaFree of a few hundred MB cost more than a whole query                 */
+  size_t cap_points, cap_mean, cap_bases, cap_graph, *cap_tab, cap_tries;
 } device_index;
 
 static device_index IDX;
@@ -66,14 +69,55 @@ static uint64_t fingerprint(const save_t *s, const ftype *points) {
   return h;
 }
 
+static void reserve(void **ptr, size_t *cap, size_t bytes) {
+  if (bytes <= *cap && *ptr) return;
+  if (*ptr) {
+    CK(cudaStreamSynchronize((cudaStream_t)annh_stream()));
+    CK(cudaFree(*ptr));
+  }
+  CK(cudaMalloc(ptr, bytes ? bytes : 1));
+  *cap = bytes ? bytes : 1;
+}
+
+/* forget the current index; its device buffers stay allocated for the next one */
 static void drop_index(void) {
-  if (!IDX.live) return;
+  IDX.live = 0;
+  IDX.graph_key = NULL;
+  IDX.points_key = NULL;
+}
+
+/* gpu_cleanup(): really give the memory back */
+static void release_index(void) {
   CK(cudaStreamSynchronize((cudaStream_t)annh_stream()));
-  CK(cudaFree(IDX.d_points)); CK(cudaFree(IDX.d_mean)); CK(cudaFree(IDX.d_bases));
-  CK(cudaFree(IDX.d_graph));
-  for (size_t t = 0; t < IDX.tries; t++) CK(cudaFree(IDX.d_tab[t]));
+  if (IDX.d_points) CK(cudaFree(IDX.d_points));
+  if (IDX.d_mean) CK(cudaFree(IDX.d_mean));
+  if (IDX.d_bases) CK(cudaFree(IDX.d_bases));
+  if (IDX.d_graph) CK(cudaFree(IDX.d_graph));
+  for (size_t t = 0; t < IDX.cap_tries; t++)
+    if (IDX.d_tab[t]) CK(cudaFree(IDX.d_tab[t]));
   free(IDX.d_tab);
+  free(IDX.cap_tab);
   memset(&IDX, 0, sizeof IDX);
+}
+
+static void reserve_index(size_t n, size_t k, size_t d_short, size_t d, size_t tries) {
+  const size_t w = sizeof(ftype);
+  drop_index();
+  IDX.n = n; IDX.k = k; IDX.d_short = d_short; IDX.d = d; IDX.tries = tries;
+  reserve((void **)&IDX.d_points, &IDX.cap_points, n * d * w);
+  reserve((void **)&IDX.d_mean, &IDX.cap_mean, d * w);
+  reserve((void **)&IDX.d_bases, &IDX.cap_bases, (tries * d_short * d + 1) * w);
+  reserve((void **)&IDX.d_graph, &IDX.cap_graph, n * k * 4);
+  if (tries > IDX.cap_tries) {
+    IDX.d_tab = realloc(IDX.d_tab, tries * sizeof(annb_u32 *));
+    IDX.cap_tab = realloc(IDX.cap_tab, tries * sizeof(size_t));
+    for (size_t t = IDX.cap_tries; t < tries; t++) { IDX.d_tab[t] = NULL; IDX.cap_tab[t] = 0; }
+    IDX.cap_tries = tries;
+  }
+  if (!cleanup_registered) {
+    register_cleanup(release_index);
+    cleanup_registered = 1;
+  }
 }
 
 void annh_forget_save(const save_t *save) {
@@ -86,21 +130,13 @@ static void upload_narrow(const size_t *host, size_t count, annb_u32 *dst, size_
 }
 
 static void build_index(const save_t *s, const ftype *points, uint64_t fp) {
-  drop_index();
   cudaStream_t st = (cudaStream_t)annh_stream();
   const size_t w = sizeof(ftype), T = (size_t)s->tries, B = (size_t)1 << s->d_short;
-  IDX.graph_key = s->graph; IDX.points_key = points;
-  IDX.n = s->n; IDX.k = s->k; IDX.d_short = s->d_short; IDX.d = s->d_long; IDX.tries = T;
-  IDX.fingerprint = fp;
-  CK(cudaMalloc((void **)&IDX.d_points, s->n * s->d_long * w));
-  CK(cudaMalloc((void **)&IDX.d_mean, s->d_long * w));
-  CK(cudaMalloc((void **)&IDX.d_bases, (T * s->d_short * s->d_long + 1) * w));
-  CK(cudaMalloc((void **)&IDX.d_graph, s->n * s->k * 4));
-  IDX.d_tab = calloc(T, sizeof(annb_u32 *));
+  reserve_index(s->n, s->k, s->d_short, s->d_long, T);
   size_t tmp_cells = s->n * s->k;
   for (size_t t = 0; t < T; t++) {
     size_t cells = B * s->par_maxes[t];
-    CK(cudaMalloc((void **)&IDX.d_tab[t], (cells ? cells : 1) * 4));
+    reserve((void **)&IDX.d_tab[t], &IDX.cap_tab[t], cells * 4);
     if (cells > tmp_cells) tmp_cells = cells;
   }
   size_t *tmp = NULL;
@@ -112,11 +148,46 @@ static void build_index(const save_t *s, const ftype *points, uint64_t fp) {
   for (size_t t = 0; t < T; t++) upload_narrow(s->which_par[t], B * s->par_maxes[t], IDX.d_tab[t], tmp, st);
   CK(cudaStreamSynchronize(st));
   CK(cudaFree(tmp));
+  IDX.graph_key = s->graph; IDX.points_key = points;
+  IDX.fingerprint = fp;
   IDX.live = 1;
-  if (!cleanup_registered) {
-    register_cleanup(drop_index);
-    cleanup_registered = 1;
-  }
+}
+
+/* ---- adoption: precomp_gpu(save != NULL) leaves the index on the device -------------------
+ * Everything query_gpu needs already sits in device memory at the end of precomp (points,
+ * merged graph, bucket tables), so it is copied device-to-device into the cache instead of
+ * being uploaded again by the first query.                                                 */
+static int cache_enabled(void) {
+  const char *env = getenv("ANN_B200_QUERY_CACHE");
+  return !(env && *env == '0');
+}
+
+int annh_index_adopt_begin(size_t n, size_t k, size_t d_short, size_t d, size_t tries) {
+  if (!cache_enabled()) return 0;
+  reserve_index(n, k, d_short, d, tries);
+  return 1;
+}
+
+/* dev_table: the size_t table of try t as exported for save->which_par[t] (still on the device) */
+void annh_index_adopt_table(int t, const size_t *dev_table, size_t cells) {
+  cudaStream_t st = (cudaStream_t)annh_stream();
+  reserve((void **)&IDX.d_tab[t], &IDX.cap_tab[t], cells * 4);
+  annb_narrow_ids(dev_table, cells, IDX.d_tab[t], st);
+}
+
+void annh_index_adopt_finish(const save_t *s, const ftype *host_points, const ftype *dev_points,
+                             const ftype *dev_mean, const annb_u32 *dev_graph) {
+  cudaStream_t st = (cudaStream_t)annh_stream();
+  const size_t w = sizeof(ftype);
+  CK(cudaMemcpyAsync(IDX.d_points, dev_points, s->n * s->d_long * w, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(IDX.d_mean, dev_mean, s->d_long * w, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(IDX.d_bases, s->bases, (size_t)s->tries * s->d_short * s->d_long * w, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(IDX.d_graph, dev_graph, s->n * s->k * 4, cudaMemcpyDeviceToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  IDX.graph_key = s->graph;
+  IDX.points_key = host_points;
+  IDX.fingerprint = fingerprint(s, host_points);
+  IDX.live = 1;
 }
 
 size_t *query_gpu(const save_t *save, const ftype *points, size_t ycnt, const ftype *y,
@@ -131,8 +202,7 @@ size_t *query_gpu(const save_t *save, const ftype *points, size_t ycnt, const ft
     if (dists_o) *dists_o = malloc(1);
     return malloc(1);
   }
-  const char *env = getenv("ANN_B200_QUERY_CACHE");
-  int use_cache = !(env && *env == '0');
+  int use_cache = cache_enabled();
   uint64_t fp = fingerprint(save, points);
   if (!(use_cache && IDX.live && IDX.graph_key == save->graph && IDX.points_key == points &&
         IDX.n == n && IDX.k == k && IDX.d_short == ds && IDX.d == d && IDX.tries == T &&
