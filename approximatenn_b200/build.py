@@ -18,7 +18,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CU_SOURCES = ["annb_prepare.cu", "annb_leaf.cu", "annb_finish.cu", "annb_query.cu"]
 C_SOURCES = ["ann_host.c", "ann_results.c", "ann_ingest.c", "ann_query.c", "ann_dist.c", "ann_save_io.c"]
 HEADERS = [os.path.join(INCLUDE, h) for h in os.listdir(INCLUDE)] + [
-    os.path.join(CSRC, "ann_host.h"), os.path.join(CSRC, "annb_common.cuh")]
+    os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".h", ".cuh"))]
 
 
 def lib_path(suffix: str) -> str:

@@ -400,7 +400,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   desc.inv_sqrt2 = 1 / sqrt(2.0);
   const size_t list_bytes = n * k * (4 + w);                   /* one per-try list      */
   const size_t np = annh_dist_padded_rows(n);                  /* rows of all-gathered arrays */
-  const size_t scratch_bytes = annb_leaf_scratch_bytes(n);
+  const size_t scratch_bytes = annb_leaf_scratch_bytes(n, d, d_short, k);
   size_t fixed = pad256(np * d * w) + pad256(n * d * w) + pad256(d * w) + pad256(Tl * n * 4 + 4) +
                  pad256(buckets * 4) + pad256((buckets + 1) * 4) + pad256(n * 4) * 2 +
                  pad256(T * 4) + pad256(annb_scan_tmp_bytes(buckets)) +
@@ -548,7 +548,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
       annb_gather_rows(dX, dorder, n, d, dXs, st);
       span_end(sp);
       sp = span_begin(4);
-      annb_leaf_topk(dXs, dorder, doffset, hash_t, dtmax + t, n, d, d_short, k, dl_ids + j * n * k,
+      annb_leaf_topk(dXs, dmean, dorder, doffset, hash_t, dtmax + t, n, d, d_short, k, dl_ids + j * n * k,
                      dl_dist + j * n * k, dscratch, dstatus, st);
       span_end(sp);
       admit[j] = annb200_dist_admit(k, tries, (int)t);

@@ -19,6 +19,23 @@
 #include "annb200.h"
 #include "ann_host.h"
 
+#include <time.h>
+static double q_now_ms(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+/* ANN_B200_HOSTPROF=1: phase times of query_gpu on stderr (synchronises after each phase) */
+#define QP(label)                                                                       \
+  do {                                                                                  \
+    if (qprof) {                                                                        \
+      cudaStreamSynchronize(st);                                                        \
+      double t_ = q_now_ms();                                                           \
+      fprintf(stderr, "[queryprof] %-22s +%8.3f ms\n", label, t_ - qlast);              \
+      qlast = t_;                                                                       \
+    }                                                                                   \
+  } while (0)
+
 #define CK(call)                                                                        \
   do {                                                                                  \
     cudaError_t e_ = (call);                                                            \
@@ -194,6 +211,9 @@ size_t *query_gpu(const save_t *save, const ftype *points, size_t ycnt, const ft
                   ftype **dists_o) {
   gpu_init();
   cudaStream_t st = (cudaStream_t)annh_stream();
+  const char *qenv = getenv("ANN_B200_HOSTPROF");
+  const int qprof = qenv && *qenv && *qenv != '0';
+  double qlast = q_now_ms();
   const size_t n = save->n, k = save->k, d = save->d_long, ds = save->d_short, w = sizeof(ftype);
   const size_t T = (size_t)save->tries;
   if (n >= 0xFFFFFFFFull) annh_fatal("%s", "n must be below 2^32 - 1");
@@ -208,6 +228,7 @@ size_t *query_gpu(const save_t *save, const ftype *points, size_t ycnt, const ft
         IDX.n == n && IDX.k == k && IDX.d_short == ds && IDX.d == d && IDX.tries == T &&
         IDX.fingerprint == fp))
     build_index(save, points, fp);
+  QP("fingerprint+index");
 
   annh_egress *eg = annh_egress_begin(ycnt, k, dists_o != NULL, 0, annh_device());
   const size_t scratch_bytes = ycnt * 4 + 1024 + ((size_t)64 << 20);
@@ -227,10 +248,13 @@ size_t *query_gpu(const save_t *save, const ftype *points, size_t ycnt, const ft
   if (same_set && ycnt <= n) dq = IDX.d_points;
   else CK(cudaMemcpyAsync(dy, y, ycnt * d * w, cudaMemcpyHostToDevice, st));
 
+  QP("alloc+upload y");
   annb_query_hash(dq, IDX.d_mean, IDX.d_bases, ycnt, d, ds, (int)T, dsign, st);
+  QP("query_hash");
   annb_query_rows(dq, IDX.d_points, (const annb_u32 *const *)IDX.d_tab, save->par_maxes, (int)T,
                   dsign, n, ycnt, d, ds, k, same_set, down_ids, down_dist, dscratch, scratch_bytes,
                   dstatus, st);
+  QP("query_rows");
   int nch = annh_egress_chunks(eg);
   for (int c = 0; c < nch; c++) {
     size_t r0 = (ycnt * (size_t)c / nch) & ~(size_t)31;
@@ -243,7 +267,9 @@ size_t *query_gpu(const save_t *save, const ftype *points, size_t ycnt, const ft
   int h_status = 0;
   CK(cudaMemcpyAsync(&h_status, dstatus, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  QP("supercharge");
   size_t *result = annh_egress_end(eg, dists_o, NULL);
+  QP("egress_end");
   if (h_status) annh_fatal("%s", "scratch too small for a literal candidate row");
   if (!use_cache) drop_index();
   return result;

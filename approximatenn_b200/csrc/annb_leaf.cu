@@ -12,6 +12,7 @@
 //   leaf_literal_kernel     redoes the (rare) rows in which an exact distance tie could
 //                           matter with the reference's literal row + sorting network.
 #include "annb_common.cuh"
+#include <cuda_bf16.h>
 
 static __device__ unsigned long long leaf_literal_rows_dev;
 static __device__ unsigned long long leaf_pairs_dev;      // (point, real candidate) pairs measured by S3
@@ -271,7 +272,8 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
                       const u32 *__restrict__ offset, const u32 *__restrict__ tmax_p, size_t n,
                       size_t buckets, int d_short, int k, u32 *__restrict__ list_ids,
                       FT *__restrict__ list_dist, TieList ties, int pack_tries, int max_slices,
-                      unsigned long long negzero2, u32 *__restrict__ ticket) {
+                      unsigned long long negzero2, u32 *__restrict__ ticket,
+                      const u32 *__restrict__ bucket_list, const u32 *__restrict__ bucket_count) {
   typedef TileSmem<D, KC, B> SM;
   constexpr int RS = SM::RS;
   constexpr int PPR = D / VW;                                          // 16-byte pieces per row
@@ -292,7 +294,9 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
   size_t b = 0;
   if (lane == 0) b = atomicAdd(ticket, 1u);
   b = __shfl_sync(FULL, (u32)b, 0);
-  if (b >= buckets) return;
+  // with a bucket list (the buckets the screened kernel handed over) tickets index the list
+  if (b >= (bucket_list ? (size_t)*bucket_count : buckets)) return;
+  if (bucket_list) b = bucket_list[b];
   const u32 beg = offset[b], Q = offset[b + 1] - beg;
   if (Q == 0) continue;
   const unsigned long long tmax = *tmax_p;
@@ -487,6 +491,11 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
   }   // next ticket
 }
 
+#ifdef USE_FLOAT
+#include "annb_leaf_screen.cuh"
+#endif
+
+
 // =====================================================================================
 // literal rows for reported points (exact ties)
 // =====================================================================================
@@ -595,7 +604,7 @@ static void launch_warp_r(int regs, dim3 grid, dim3 block, size_t smem, annb_str
 template <int D, int KC, int B, int REGS>
 static void launch_tile(annb_stream stream, const FT *sp, const u32 *order, const u32 *offset,
                         const u32 *tmax, size_t n, size_t buckets, int d_short, int k, u32 *ids,
-                        FT *dist, TieList flags) {
+                        FT *dist, TieList flags, const u32 *bucket_list, const u32 *bucket_count) {
   size_t smem = TileSmem<D, KC, B>::per_warp * TILE_WARPS;
   static bool configured = false;
   if (!configured) {
@@ -610,7 +619,7 @@ static void launch_tile(annb_stream stream, const FT *sp, const u32 *order, cons
     unsigned resident = (unsigned)sms * 16;                 // more CTAs than can be resident: all SMs stay full
     if (grid > resident) grid = resident;
   }
-  u32 *ticket = flags.count + 32;                           // spare words of the tie-list header
+  u32 *ticket = flags.count + (bucket_list ? 33 : 32);      // spare words of the tie-list header
   RT_CHECK(cudaMemsetAsync(ticket, 0, sizeof(u32), stream));
   static int pack_tries = -1, max_slices = 16;
   if (pack_tries < 0) {
@@ -621,17 +630,18 @@ static void launch_tile(annb_stream stream, const FT *sp, const u32 *order, cons
     if (max_slices < 1) max_slices = 1;
     if (max_slices > 16) max_slices = 16;
   }
-  leaf_topk_tile_kernel<D, KC, B, REGS><<<grid, TILE_WARPS * 32, smem, stream>>>(sp, order, offset, tmax, n, buckets, d_short, k, ids, dist, flags, pack_tries, max_slices, 0x8000000080000000ull, ticket);
+  leaf_topk_tile_kernel<D, KC, B, REGS><<<grid, TILE_WARPS * 32, smem, stream>>>(sp, order, offset, tmax, n, buckets, d_short, k, ids, dist, flags, pack_tries, max_slices, 0x8000000080000000ull, ticket, bucket_list, bucket_count);
 }
 
 // returns false when no tiled instantiation covers (d, k)
 static bool try_launch_tile(annb_stream stream, const FT *sp, const u32 *order, const u32 *offset,
                             const u32 *tmax, size_t n, size_t buckets, size_t d, int d_short,
-                            size_t k, u32 *ids, FT *dist, TieList flags) {
+                            size_t k, u32 *ids, FT *dist, TieList flags,
+                            const u32 *bucket_list = NULL, const u32 *bucket_count = NULL) {
   const char *off = getenv("ANN_B200_NO_TILE");
-  if (off && *off && *off != '0') return false;
+  if (off && *off && *off != '0' && !bucket_list) return false;
   if (d_short > 31) return false;
-#define TILE_CASE(DD, KK, BB, MB) { launch_tile<DD, KK, BB, MB>(stream, sp, order, offset, tmax, n, buckets, d_short, (int)k, ids, dist, flags); return true; }
+#define TILE_CASE(DD, KK, BB, MB) { launch_tile<DD, KK, BB, MB>(stream, sp, order, offset, tmax, n, buckets, d_short, (int)k, ids, dist, flags, bucket_list, bucket_count); return true; }
   if (k <= 16) {
     if (d == 16) TILE_CASE(16, 16, 16, 128)
     if (d == 32) TILE_CASE(32, 16, 16, 128)
@@ -649,18 +659,106 @@ static bool try_launch_tile(annb_stream stream, const FT *sp, const u32 *order, 
   return false;
 }
 
-extern "C" size_t annb_leaf_scratch_bytes(size_t n) { return 2 * n * sizeof(u32) + (64u << 20) + 1024; }
+static size_t literal_area_bytes(size_t n) { return 3 * n * sizeof(u32) + (64u << 20) + 1024; }
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+static bool screen_covers(size_t d, size_t d_short, size_t k) {
+#ifdef USE_FLOAT
+  return (d == 16 || d == 32 || d == 64) && k <= 16 && d_short >= 1 && d_short <= 31;
+#else
+  (void)d; (void)d_short; (void)k;
+  return false;
+#endif
+}
+// fp16 copy, norms, scale word and the overflow bucket list of the screened path
+static size_t screen_area_bytes(size_t n, size_t d, size_t d_short, size_t k) {
+  if (!screen_covers(d, d_short, k)) return 0;
+  return align256(n * d * 2) + align256(n * 8) + 256 + align256(((size_t)4 << d_short) + 4);
+}
+extern "C" size_t annb_leaf_scratch_bytes(size_t n, size_t d, size_t d_short, size_t k) {
+  return align256(literal_area_bytes(n)) + screen_area_bytes(n, d, d_short, k);
+}
 
-extern "C" void annb_leaf_topk(const FT *sorted_points, const u32 *order, const u32 *offset,
-                               const u32 *hash, const u32 *tmax, size_t n, size_t d,
-                               size_t d_short, size_t k, u32 *list_ids, FT *list_dist,
+#ifdef USE_FLOAT
+static int screen_enabled() {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char *e = getenv("ANN_B200_SCREEN");
+    enabled = (e && *e) ? (*e != '0') : 0;
+  }
+  return enabled;
+}
+
+template <int D>
+static void launch_screen(annb_stream stream, const FT *sp, const FT *mean, unsigned char *area,
+                          const u32 *order, const u32 *offset, const u32 *tmax, size_t n,
+                          size_t buckets, int d_short, int k, u32 *ids, FT *dist, TieList flags,
+                          ScreenOverflow *ovf_out) {
+  unsigned short *sp16 = reinterpret_cast<unsigned short *>(area);
+  float2 *nrm = reinterpret_cast<float2 *>(area + align256(n * (size_t)D * 2));
+  unsigned *words = reinterpret_cast<unsigned *>(area + align256(n * (size_t)D * 2) + align256(n * 8));
+  unsigned *maxbits = words;                                  // words[0]: max |x - mean|, words[1]: overflow count
+  ScreenOverflow ovf;
+  ovf.count = words + 1;
+  ovf.buckets = words + 64;
+  RT_CHECK(cudaMemsetAsync(words, 0, 8, stream));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  screen_maxabs_kernel<<<sms * 8, 256, 0, stream>>>(sp, mean, n, D, maxbits);
+  LAUNCH_CHECK("screen_maxabs");
+  screen_prep_kernel<<<grid_for(n * (D / 4), 256), 256, 0, stream>>>(sp, mean, n, D, maxbits, sp16, nrm);
+  LAUNCH_CHECK("screen_prep");
+  // shared-memory tables sized for 1.25x the expected candidate count; bigger buckets go to the tiled kernel
+  double expect = (double)(d_short + 1) * ((double)n / (double)buckets);
+  size_t want = (size_t)(1.25 * expect) + 48;
+  int ct = (int)(((want + 55) / 64) * 64 + 8);               // = 8 mod 64: conflict-free parking of the bounds
+  if (ct > 1032) ct = 1032;
+  if (ct < screen_min_ct(ScreenOverlay<D>::bytes)) ct = screen_min_ct(ScreenOverlay<D>::bytes);
+  size_t smem = screen_smem_bytes(ct);
+  static bool configured = false;
+  if (!configured) {
+    RT_CHECK(cudaFuncSetAttribute(leaf_screen_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)screen_smem_bytes(1032)));
+    configured = true;
+  }
+  unsigned grid = (unsigned)buckets;
+  unsigned resident = (unsigned)sms * 16;
+  if (grid > resident) grid = resident;
+  u32 *ticket = flags.count + 32;
+  RT_CHECK(cudaMemsetAsync(ticket, 0, sizeof(u32), stream));
+  leaf_screen_kernel<D><<<grid, 32, smem, stream>>>(sp, sp16, nrm, order, offset, tmax, n, buckets, d_short, k, ids, dist, flags, 0x8000000080000000ull, ticket, ct, ovf, getenv("ANN_B200_SCREEN_DBG") ? atoi(getenv("ANN_B200_SCREEN_DBG")) : 0);
+  LAUNCH_CHECK("leaf_screen");
+  *ovf_out = ovf;
+}
+
+// returns false when the screened path does not cover (d, k) or is switched off
+static bool try_launch_screen(annb_stream stream, const FT *sp, const FT *mean, unsigned char *area,
+                              const u32 *order, const u32 *offset, const u32 *tmax, size_t n,
+                              size_t buckets, size_t d, int d_short, size_t k, u32 *ids, FT *dist,
+                              TieList flags) {
+  if (!screen_enabled() || !screen_covers(d, (size_t)d_short, k)) return false;
+  ScreenOverflow ovf;
+  if (d == 16) launch_screen<16>(stream, sp, mean, area, order, offset, tmax, n, buckets, d_short, (int)k, ids, dist, flags, &ovf);
+  else if (d == 32) launch_screen<32>(stream, sp, mean, area, order, offset, tmax, n, buckets, d_short, (int)k, ids, dist, flags, &ovf);
+  else launch_screen<64>(stream, sp, mean, area, order, offset, tmax, n, buckets, d_short, (int)k, ids, dist, flags, &ovf);
+  // buckets the screen could not hold: the tiled kernel, driven by the list
+  if (!try_launch_tile(stream, sp, order, offset, tmax, n, buckets, d, d_short, k, ids, dist, flags, ovf.buckets, ovf.count))
+    fatal_config("screened leaf path without a tiled kernel for the same shape");
+  return true;
+}
+#endif
+
+extern "C" void annb_leaf_topk(const FT *sorted_points, const FT *mean, const u32 *order,
+                               const u32 *offset, const u32 *hash, const u32 *tmax, size_t n,
+                               size_t d, size_t d_short, size_t k, u32 *list_ids, FT *list_dist,
                                void *scratch, int *status, annb_stream stream) {
   int regs = list_regs(k);
   if (!regs) fatal_config("k > 256");
   // scratch layout: rank_of[n] | tie list (count, rows[n]) | literal-row slabs
   u32 *rank_of = (u32 *)scratch;
   const size_t rank_bytes = (n * sizeof(u32) + 255) & ~(size_t)255;
-  LiteralScratch ls = carve_literal_scratch((unsigned char *)scratch + rank_bytes, annb_leaf_scratch_bytes(n) - rank_bytes, n);
+  LiteralScratch ls = carve_literal_scratch((unsigned char *)scratch + rank_bytes, literal_area_bytes(n) - rank_bytes, 2 * n);
+  unsigned char *screen_area = (unsigned char *)scratch + align256(literal_area_bytes(n));
+  (void)screen_area; (void)mean;
   TieList flags = ls.list;
   unsigned char *slabs = ls.slabs;
   size_t slab_bytes = ls.slab_bytes;
@@ -670,8 +768,13 @@ extern "C" void annb_leaf_topk(const FT *sorted_points, const u32 *order, const 
   size_t gsmem = mode ? 0 : 8 * d * sizeof(FT);
   if (gsmem > 200 * 1024) fatal_config("d too large for the generic distance path");
 
-  if (!try_launch_tile(stream, sorted_points, order, offset, tmax, n, buckets, d, (int)d_short, k,
-                       list_ids, list_dist, flags)) {
+  bool done = false;
+#ifdef USE_FLOAT
+  done = try_launch_screen(stream, sorted_points, mean, screen_area, order, offset, tmax, n, buckets, d,
+                           (int)d_short, k, list_ids, list_dist, flags);
+#endif
+  if (!done && !try_launch_tile(stream, sorted_points, order, offset, tmax, n, buckets, d, (int)d_short, k,
+                                list_ids, list_dist, flags)) {
     dim3 block(256), grid(grid_for(n * 32, 256));
 #define W_ARGS regs, grid, block, gsmem, stream, sorted_points, order, offset, hash, tmax, n, (int)d, (int)d_short, (int)k, list_ids, list_dist, flags
     switch (mode) {

@@ -92,11 +92,13 @@ void annb_export_table(const annb_u32 *offset, const annb_u32 *order, size_t n, 
  * P = 2^floor(log2((d_short+1)*tmax)) — the reference's prefix rule (SURVEY §8.A.3 rule 5).
  * list_ids/list_dist: [n][k], ascending squared distance, (n, +inf) where fewer than k
  * finite candidates exist.  `tmax` is read on the device.
- * scratch: annb_leaf_scratch_bytes(n) bytes.                                               */
-size_t annb_leaf_scratch_bytes(size_t n);
-void annb_leaf_topk(const ftype *sorted_points, const annb_u32 *order, const annb_u32 *offset,
-                    const annb_u32 *hash, const annb_u32 *tmax, size_t n, size_t d,
-                    size_t d_short, size_t k, annb_u32 *list_ids, ftype *list_dist,
+ * `mean` (d entries, may be NULL) only recentres the low-precision copy the screened path
+ * brackets distances with; it never enters a reported distance.
+ * scratch: annb_leaf_scratch_bytes(n, d, d_short, k) bytes.                                */
+size_t annb_leaf_scratch_bytes(size_t n, size_t d, size_t d_short, size_t k);
+void annb_leaf_topk(const ftype *sorted_points, const ftype *mean, const annb_u32 *order,
+                    const annb_u32 *offset, const annb_u32 *hash, const annb_u32 *tmax, size_t n,
+                    size_t d, size_t d_short, size_t k, annb_u32 *list_ids, ftype *list_dist,
                     void *scratch, int *status, annb_stream stream);
 
 /* ---- S4: merge of the per-try lists (first sort_and_uniq of det_results, alg.c:312) ----
@@ -151,6 +153,10 @@ void annb_narrow_ids(const size_t *src, size_t count, annb_u32 *dst, annb_stream
 /* (point, real candidate) pairs whose distance S3 evaluated since the last reset (synchronous);
  * 3*d floating-point operations each (compute.cl:147-166) — the flop count of the leaf stage     */
 unsigned long long annb_leaf_pairs(int reset);
+/* of those, the pairs the screened path sent through the exact tree (0 when it is off)          */
+unsigned long long annb_leaf_exact_pairs(int reset);
+/* buckets the screened path handed to the tiled kernel (tables or survivor lists too small)     */
+unsigned long long annb_leaf_overflow_buckets(int reset);
 
 /* rows redone by the literal kernels since the last reset: [0] S3, [1] S4, [2] S5 (synchronous)  */
 void annb_literal_rows(unsigned long long out[3], int reset);
