@@ -669,6 +669,11 @@ static bool screen_covers(size_t d, size_t d_short, size_t k) {
   return false;
 #endif
 }
+#ifndef USE_FLOAT
+extern "C" void annb_leaf_screen_mode(int on) { (void)on; }
+extern "C" unsigned long long annb_leaf_exact_pairs(int reset) { (void)reset; return 0; }
+extern "C" unsigned long long annb_leaf_overflow_buckets(int reset) { (void)reset; return 0; }
+#endif
 // fp16 copy, norms, scale word and the overflow bucket list of the screened path
 static size_t screen_area_bytes(size_t n, size_t d, size_t d_short, size_t k) {
   if (!screen_covers(d, d_short, k)) return 0;
@@ -679,13 +684,18 @@ extern "C" size_t annb_leaf_scratch_bytes(size_t n, size_t d, size_t d_short, si
 }
 
 #ifdef USE_FLOAT
+// The screened path is the default where it applies; ANN_B200_SCREEN=0 (or annb_leaf_screen_mode(0))
+// sends everything through the tiled kernel instead.  Both produce the same lists.
+static int screen_mode = -1;
+extern "C" void annb_leaf_screen_mode(int on) { screen_mode = on ? 1 : 0; }
 static int screen_enabled() {
-  static int enabled = -1;
-  if (enabled < 0) {
+  if (screen_mode < 0) {
     const char *e = getenv("ANN_B200_SCREEN");
-    enabled = (e && *e) ? (*e != '0') : 0;
+    screen_mode = (e && *e) ? (*e != '0') : 1;
+    const char *nt = getenv("ANN_B200_NO_TILE");            // asking for the generic kernel switches both off
+    if (nt && *nt && *nt != '0') screen_mode = 0;
   }
-  return enabled;
+  return screen_mode;
 }
 
 template <int D>

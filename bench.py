@@ -318,6 +318,10 @@ def main():
     gpu.lib.annb_launch_count(1)
     gpu.lib.annb_leaf_pairs.restype = ctypes.c_ulonglong
     gpu.lib.annb_leaf_pairs(1)
+    gpu.lib.annb_leaf_exact_pairs.restype = ctypes.c_ulonglong
+    gpu.lib.annb_leaf_overflow_buckets.restype = ctypes.c_ulonglong
+    gpu.lib.annb_leaf_exact_pairs(1)
+    gpu.lib.annb_leaf_overflow_buckets(1)
     # timed region 1: K steps with per-stage CUDA events on the library stream -> `value`
     barrier()
     t0 = time.perf_counter()
@@ -326,6 +330,8 @@ def main():
     wall_instrumented = time.perf_counter() - t0
     launches = int(gpu.lib.annb_launch_count(0))
     leaf_pairs = int(gpu.lib.annb_leaf_pairs(0)) / args.steps        # per step, this rank
+    exact_pairs = int(gpu.lib.annb_leaf_exact_pairs(0)) / args.steps  # of those, sent through the exact tree
+    overflow_buckets = int(gpu.lib.annb_leaf_overflow_buckets(0)) / args.steps
     # timed region 2: the same K steps through the C-ABI with the event instrumentation off -> `e2e`
     gpu.lib.annh_set_timing(0)
     step()
@@ -358,19 +364,25 @@ def main():
     mean_stage = {k_: statistics.mean(s[k_] for s in stages) for k_ in stages[0]}
     peak, peak_src = measured_peaks()
     dev_mean = statistics.mean(dev_ms)
-    # --- dominant kernel: leaf_topk_tile_kernel (S3), FP32-pipe bound.  Algorithmic work per
-    # (point, candidate) pair = d subtractions + d multiplications + d-1 additions, each rounded
-    # separately (the reference's arithmetic, compute.cl:147-166; an FMA would change its bits),
-    # counted as 3*d flops.  Peak = one rounded FP32 operation per lane per clock:
-    # 148 SMs x 128 lanes x max SM clock (half of the usual FFMA-counts-two figure).
+    # --- dominant kernel: S3 (leaf_screen_kernel, or leaf_topk_tile_kernel where the screen does
+    # not apply).  Algorithmic work per (point, candidate) pair = d subtractions + d multiplications
+    # + d-1 additions, each rounded separately (the reference's arithmetic, compute.cl:147-166; an
+    # FMA would change its bits), counted as 3*d flops.  Peak = one rounded FP32
+    # operation per lane per clock: 148 SMs x 128 lanes x max SM clock (half of the usual
+    # FFMA-counts-two figure).  The screened kernel reaches its rate by NOT executing most of these
+    # flops: fp16 tensor-core brackets leave `exact_pairs_per_step` pairs for the exact tree, so
+    # `frac` is algorithmic work over peak, not pipe utilisation (ncu: profiles/).
     leaf_s = mean_stage["leaf"] / 1e3
     fp32_peak = 148 * 128 * 1.965e9 / 1e12
     leaf_tflops = 3 * d * leaf_pairs / leaf_s / 1e12 if leaf_s > 0 else 0.0
-    roofline = {"kernel": "leaf_topk_tile_kernel (S3, summed over the tries of one step; includes its literal redo)",
+    screened = exact_pairs > 0
+    roofline = {"kernel": ("leaf_screen_kernel" if screened else "leaf_topk_tile_kernel") +
+                          " (S3, summed over the tries of one step; includes prep and literal redo)",
                 "bound": "fp32", "achieved": leaf_tflops, "peak": fp32_peak,
                 "peak_source": "148 SM x 128 lanes x 1.965 GHz, one separately rounded FP32 op per lane-clock",
                 "unit": "TFLOP/s", "frac": leaf_tflops / fp32_peak, "traffic": None,
                 "pairs_per_step": leaf_pairs, "flops_per_pair": 3 * d,
+                "exact_pairs_per_step": exact_pairs, "screen_overflow_buckets_per_step": overflow_buckets,
                 "share_of_device_time": mean_stage["leaf"] / dev_mean}
     # --- dominant HBM-bound kernel: supercharge.  Algorithmic bytes per launch set:
     # rows*(P2-k) gathered vectors of (4 + d*w) B, + own lists in, + ids and dists out.

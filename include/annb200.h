@@ -157,6 +157,9 @@ unsigned long long annb_leaf_pairs(int reset);
 unsigned long long annb_leaf_exact_pairs(int reset);
 /* buckets the screened path handed to the tiled kernel (tables or survivor lists too small)     */
 unsigned long long annb_leaf_overflow_buckets(int reset);
+/* 1 (default): float rows with d in {16, 32, 64} and k <= 16 take the screened S3 path;
+ * 0: the tiled kernel only.  The lists are identical either way (tests compare them).          */
+void annb_leaf_screen_mode(int on);
 
 /* rows redone by the literal kernels since the last reset: [0] S3, [1] S4, [2] S5 (synchronous)  */
 void annb_literal_rows(unsigned long long out[3], int reset);
