@@ -407,7 +407,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
                  pad256(Tl * planes * 2 * 4 + 4) + pad256(Tl * planes * 2 * w + w) +
                  pad256(Tl * d_max * 4 + 4) + pad256(Tl * d_short * 4 + 4) +
                  pad256(annb_hash_scratch_bytes(&desc)) +
-                 pad256(scratch_bytes) + 8192;
+                 pad256(scratch_bytes) + 8192 + 256;
   if (sharded && save) fixed += pad256(T * n * 4);            /* every try's hashes, for the tables */
   if (sharded)   /* merged ids (all rows), merged dists + results (own rows), exchanged lists */
     fixed += pad256(np * k * 4) + pad256(my_rows * k * w) + pad256(my_rows * k * 4) + pad256(my_rows * k * w) +
@@ -451,6 +451,8 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   ftype *dout_dist = annh_arena_take(out_cap * k * w);
   void *dscratch = annh_arena_take(scratch_bytes);
   int *dstatus = annh_arena_take(sizeof(int));
+  unsigned *dscreen = annh_arena_take(256);                     /* scale word of the screened S3 path */
+  const int screened = annb_screen_applies(d, d_short, k);
   annb_u32 *dhash_all = (sharded && save) ? annh_arena_take(T * n * 4) : NULL;
   annb_u32 *ds_ids = sharded ? annh_arena_take(T * my_rows * k * 4) : NULL;   /* [T][my_rows][k] */
   ftype *ds_dist = sharded ? annh_arena_take(T * my_rows * k * w) : NULL;
@@ -487,6 +489,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
     }
   }
   annb_scale_means(dXs, n, d, dmean, st);
+  if (screened && Tl) annb_screen_scale(dX, dmean, n, d, dscreen, st);
 
   /* 5. S1 hashes of every owned try in one pass over the points                         */
   span_end(sp);
@@ -545,11 +548,12 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
         annh_prefault(save->which_par[t], cells * sizeof(size_t));
         CK(cudaMemcpyAsync(save->which_par[t], dtable, cells * sizeof(size_t), cudaMemcpyDeviceToHost, st));
       }
-      annb_gather_rows(dX, dorder, n, d, dXs, st);
+      if (screened) annb_gather_rows_screen(dX, dorder, n, d, dmean, dscreen, dXs, dscratch, st);
+      else annb_gather_rows(dX, dorder, n, d, dXs, st);
       span_end(sp);
       sp = span_begin(4);
       annb_leaf_topk(dXs, dmean, dorder, doffset, hash_t, dtmax + t, n, d, d_short, k, dl_ids + j * n * k,
-                     dl_dist + j * n * k, dscratch, dstatus, st);
+                     dl_dist + j * n * k, dscratch, dstatus, screened ? dscreen : NULL, screened, st);
       span_end(sp);
       admit[j] = annb200_dist_admit(k, tries, (int)t);
     }

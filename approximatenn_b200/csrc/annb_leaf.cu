@@ -673,6 +673,14 @@ static bool screen_covers(size_t d, size_t d_short, size_t k) {
 extern "C" void annb_leaf_screen_mode(int on) { (void)on; }
 extern "C" unsigned long long annb_leaf_exact_pairs(int reset) { (void)reset; return 0; }
 extern "C" unsigned long long annb_leaf_overflow_buckets(int reset) { (void)reset; return 0; }
+extern "C" int annb_screen_applies(size_t d, size_t d_short, size_t k) { (void)d; (void)d_short; (void)k; return 0; }
+extern "C" void annb_screen_scale(const FT *, const FT *, size_t, size_t, unsigned *, annb_stream) {
+  fatal_config("screened leaf path in the double build");
+}
+extern "C" void annb_gather_rows_screen(const FT *, const u32 *, size_t, size_t, const FT *, const unsigned *, FT *,
+                                        void *, annb_stream) {
+  fatal_config("screened leaf path in the double build");
+}
 #endif
 // fp16 copy, norms, scale word and the overflow bucket list of the screened path
 static size_t screen_area_bytes(size_t n, size_t d, size_t d_short, size_t k) {
@@ -698,26 +706,72 @@ static int screen_enabled() {
   return screen_mode;
 }
 
-template <int D>
-static void launch_screen(annb_stream stream, const FT *sp, const FT *mean, unsigned char *area,
-                          const u32 *order, const u32 *offset, const u32 *tmax, size_t n,
-                          size_t buckets, int d_short, int k, u32 *ids, FT *dist, TieList flags,
-                          ScreenOverflow *ovf_out) {
-  unsigned short *sp16 = reinterpret_cast<unsigned short *>(area);
-  float2 *nrm = reinterpret_cast<float2 *>(area + align256(n * (size_t)D * 2));
-  unsigned *words = reinterpret_cast<unsigned *>(area + align256(n * (size_t)D * 2) + align256(n * 8));
-  unsigned *maxbits = words;                                  // words[0]: max |x - mean|, words[1]: overflow count
-  ScreenOverflow ovf;
-  ovf.count = words + 1;
-  ovf.buckets = words + 64;
-  RT_CHECK(cudaMemsetAsync(words, 0, 8, stream));
+struct ScreenArea {                                           // carved from the end of the leaf scratch
+  unsigned short *sp16;                                       // [n][d] fp16
+  float2 *nrm;                                                // [n]
+  unsigned *words;                                            // [0] max |x - mean| when not supplied, [1] overflow count
+  u32 *overflow_buckets;
+};
+static ScreenArea screen_area(void *scratch, size_t n, size_t d) {
+  unsigned char *area = (unsigned char *)scratch + align256(literal_area_bytes(n));
+  ScreenArea a;
+  a.sp16 = reinterpret_cast<unsigned short *>(area);
+  a.nrm = reinterpret_cast<float2 *>(area + align256(n * d * 2));
+  a.words = reinterpret_cast<unsigned *>(area + align256(n * d * 2) + align256(n * 8));
+  a.overflow_buckets = a.words + 64;
+  return a;
+}
+static void launch_maxabs(annb_stream stream, const FT *points, const FT *mean, size_t n, size_t d, unsigned *bits) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  screen_maxabs_kernel<<<sms * 8, 256, 0, stream>>>(sp, mean, n, D, maxbits);
+  RT_CHECK(cudaMemsetAsync(bits, 0, sizeof(unsigned), stream));
+  screen_maxabs_kernel<<<sms * 8, 256, 0, stream>>>(points, mean, n, (int)d, bits);
   LAUNCH_CHECK("screen_maxabs");
-  screen_prep_kernel<<<grid_for(n * (D / 4), 256), 256, 0, stream>>>(sp, mean, n, D, maxbits, sp16, nrm);
-  LAUNCH_CHECK("screen_prep");
+}
+
+extern "C" int annb_screen_applies(size_t d, size_t d_short, size_t k) {
+  return screen_enabled() && screen_covers(d, d_short, k);
+}
+// the fp16 scale of the whole set (the same for every try): once per precomp
+extern "C" void annb_screen_scale(const FT *points, const FT *mean, size_t n, size_t d, unsigned *scale_bits,
+                                  annb_stream stream) {
+  launch_maxabs(stream, points, mean, n, d, scale_bits);
+}
+// S2's gather fused with the preparation of the screened path (fp16 copy + norms into `leaf_scratch`)
+extern "C" void annb_gather_rows_screen(const FT *points, const u32 *order, size_t n, size_t d, const FT *mean,
+                                        const unsigned *scale_bits, FT *sorted_points, void *leaf_scratch,
+                                        annb_stream stream) {
+  ScreenArea a = screen_area(leaf_scratch, n, d);
+  screen_prep_kernel<<<grid_for(n * (d / 4), 256), 256, 0, stream>>>(points, order, sorted_points, mean, n, (int)d,
+                                                                    scale_bits, a.sp16, a.nrm);
+  LAUNCH_CHECK("gather_rows_screen");
+}
+
+template <int D>
+static void launch_screen(annb_stream stream, const FT *sp, const FT *mean, void *scratch,
+                          const unsigned *scale_bits, int rows_prepared,
+                          const u32 *order, const u32 *offset, const u32 *tmax, size_t n,
+                          size_t buckets, int d_short, int k, u32 *ids, FT *dist, TieList flags,
+                          ScreenOverflow *ovf_out) {
+  ScreenArea a = screen_area(scratch, n, D);
+  unsigned short *sp16 = a.sp16;
+  float2 *nrm = a.nrm;
+  ScreenOverflow ovf;
+  ovf.count = a.words + 1;
+  ovf.buckets = a.overflow_buckets;
+  RT_CHECK(cudaMemsetAsync(ovf.count, 0, sizeof(u32), stream));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (!rows_prepared) {
+    if (!scale_bits) {
+      launch_maxabs(stream, sp, mean, n, D, a.words);
+      scale_bits = a.words;
+    }
+    screen_prep_kernel<<<grid_for(n * (D / 4), 256), 256, 0, stream>>>(sp, NULL, NULL, mean, n, D, scale_bits, sp16, nrm);
+    LAUNCH_CHECK("screen_prep");
+  }
   // shared-memory tables sized for 1.25x the expected candidate count; bigger buckets go to the tiled kernel
   double expect = (double)(d_short + 1) * ((double)n / (double)buckets);
   size_t want = (size_t)(1.25 * expect) + 48;
@@ -741,15 +795,18 @@ static void launch_screen(annb_stream stream, const FT *sp, const FT *mean, unsi
 }
 
 // returns false when the screened path does not cover (d, k) or is switched off
-static bool try_launch_screen(annb_stream stream, const FT *sp, const FT *mean, unsigned char *area,
+static bool try_launch_screen(annb_stream stream, const FT *sp, const FT *mean, void *scratch,
+                              const unsigned *scale_bits, int rows_prepared,
                               const u32 *order, const u32 *offset, const u32 *tmax, size_t n,
                               size_t buckets, size_t d, int d_short, size_t k, u32 *ids, FT *dist,
                               TieList flags) {
   if (!screen_enabled() || !screen_covers(d, (size_t)d_short, k)) return false;
   ScreenOverflow ovf;
-  if (d == 16) launch_screen<16>(stream, sp, mean, area, order, offset, tmax, n, buckets, d_short, (int)k, ids, dist, flags, &ovf);
-  else if (d == 32) launch_screen<32>(stream, sp, mean, area, order, offset, tmax, n, buckets, d_short, (int)k, ids, dist, flags, &ovf);
-  else launch_screen<64>(stream, sp, mean, area, order, offset, tmax, n, buckets, d_short, (int)k, ids, dist, flags, &ovf);
+#define SCR_ARGS stream, sp, mean, scratch, scale_bits, rows_prepared, order, offset, tmax, n, buckets, d_short, (int)k, ids, dist, flags, &ovf
+  if (d == 16) launch_screen<16>(SCR_ARGS);
+  else if (d == 32) launch_screen<32>(SCR_ARGS);
+  else launch_screen<64>(SCR_ARGS);
+#undef SCR_ARGS
   // buckets the screen could not hold: the tiled kernel, driven by the list
   if (!try_launch_tile(stream, sp, order, offset, tmax, n, buckets, d, d_short, k, ids, dist, flags, ovf.buckets, ovf.count))
     fatal_config("screened leaf path without a tiled kernel for the same shape");
@@ -760,15 +817,15 @@ static bool try_launch_screen(annb_stream stream, const FT *sp, const FT *mean, 
 extern "C" void annb_leaf_topk(const FT *sorted_points, const FT *mean, const u32 *order,
                                const u32 *offset, const u32 *hash, const u32 *tmax, size_t n,
                                size_t d, size_t d_short, size_t k, u32 *list_ids, FT *list_dist,
-                               void *scratch, int *status, annb_stream stream) {
+                               void *scratch, int *status, const unsigned *scale_bits,
+                               int rows_prepared, annb_stream stream) {
   int regs = list_regs(k);
   if (!regs) fatal_config("k > 256");
   // scratch layout: rank_of[n] | tie list (count, rows[n]) | literal-row slabs
   u32 *rank_of = (u32 *)scratch;
   const size_t rank_bytes = (n * sizeof(u32) + 255) & ~(size_t)255;
   LiteralScratch ls = carve_literal_scratch((unsigned char *)scratch + rank_bytes, literal_area_bytes(n) - rank_bytes, 2 * n);
-  unsigned char *screen_area = (unsigned char *)scratch + align256(literal_area_bytes(n));
-  (void)screen_area; (void)mean;
+  (void)mean; (void)scale_bits; (void)rows_prepared;
   TieList flags = ls.list;
   unsigned char *slabs = ls.slabs;
   size_t slab_bytes = ls.slab_bytes;
@@ -780,8 +837,8 @@ extern "C" void annb_leaf_topk(const FT *sorted_points, const FT *mean, const u3
 
   bool done = false;
 #ifdef USE_FLOAT
-  done = try_launch_screen(stream, sorted_points, mean, screen_area, order, offset, tmax, n, buckets, d,
-                           (int)d_short, k, list_ids, list_dist, flags);
+  done = try_launch_screen(stream, sorted_points, mean, scratch, scale_bits, rows_prepared, order, offset, tmax,
+                           n, buckets, d, (int)d_short, k, list_ids, list_dist, flags);
 #endif
   if (!done && !try_launch_tile(stream, sorted_points, order, offset, tmax, n, buckets, d, (int)d_short, k,
                                 list_ids, list_dist, flags)) {

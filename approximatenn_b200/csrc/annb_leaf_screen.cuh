@@ -69,11 +69,13 @@ __device__ __forceinline__ float screen_scale(unsigned maxbits) {
   return ldexpf(1.0f, 2 - e);
 }
 
-// c = (x - mean) * scale, fp16 copy and the two norms of one row; d/4 lanes per row
+// c = (x - mean) * scale, fp16 copy and the two norms of one row; d/4 lanes per row.  With
+// `order` the row is gathered from the original array (src[order[row]]) and also written to
+// the bucket-ordered copy `sorted` — S2's gather and this preparation in one pass.
 __global__ void __launch_bounds__(256)
-screen_prep_kernel(const float *__restrict__ sp, const float *__restrict__ mean, size_t n, int d,
-                   const unsigned *__restrict__ maxbits, unsigned short *__restrict__ sp16,
-                   float2 *__restrict__ nrm) {
+screen_prep_kernel(const float *__restrict__ src, const u32 *__restrict__ order, float *__restrict__ sorted,
+                   const float *__restrict__ mean, size_t n, int d, const unsigned *__restrict__ maxbits,
+                   unsigned short *__restrict__ sp16, float2 *__restrict__ nrm) {
   const int lpr = d >> 2;
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t row = gid / lpr;
@@ -82,7 +84,9 @@ screen_prep_kernel(const float *__restrict__ sp, const float *__restrict__ mean,
   const float scale = screen_scale(*maxbits);
   float4 x = make_float4(0, 0, 0, 0), m = make_float4(0, 0, 0, 0);
   if (live) {
-    x = reinterpret_cast<const float4 *>(sp + row * (size_t)d)[l];
+    const size_t from = order ? (size_t)order[row] : row;
+    x = reinterpret_cast<const float4 *>(src + from * (size_t)d)[l];
+    if (sorted) reinterpret_cast<float4 *>(sorted + row * (size_t)d)[l] = x;
     if (mean) m = reinterpret_cast<const float4 *>(mean)[l];
   }
   float c0 = (x.x - m.x) * scale, c1 = (x.y - m.y) * scale, c2 = (x.z - m.z) * scale, c3 = (x.w - m.w) * scale;

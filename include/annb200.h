@@ -94,12 +94,31 @@ void annb_export_table(const annb_u32 *offset, const annb_u32 *order, size_t n, 
  * finite candidates exist.  `tmax` is read on the device.
  * `mean` (d entries, may be NULL) only recentres the low-precision copy the screened path
  * brackets distances with; it never enters a reported distance.
+ * scale_bits / rows_prepared: see the screened-path helpers below (NULL / 0 = annb_leaf_topk
+ * prepares everything itself).
  * scratch: annb_leaf_scratch_bytes(n, d, d_short, k) bytes.                                */
 size_t annb_leaf_scratch_bytes(size_t n, size_t d, size_t d_short, size_t k);
 void annb_leaf_topk(const ftype *sorted_points, const ftype *mean, const annb_u32 *order,
                     const annb_u32 *offset, const annb_u32 *hash, const annb_u32 *tmax, size_t n,
                     size_t d, size_t d_short, size_t k, annb_u32 *list_ids, ftype *list_dist,
-                    void *scratch, int *status, annb_stream stream);
+                    void *scratch, int *status, const unsigned *scale_bits, int rows_prepared,
+                    annb_stream stream);
+
+/* Screened S3 path (float rows, d in {16, 32, 64}, k <= 16): fp16 tensor-core brackets of every
+ * candidate distance decide which candidates go through the exact tree; the lists are the same
+ * as the tiled kernel's, bit for bit.
+ *   annb_screen_applies     1 if annb_leaf_topk will take it for this shape
+ *   annb_screen_scale       once per point set: the power-of-two scale of the fp16 copy
+ *                           (device word `scale_bits`), from max |x - mean|
+ *   annb_gather_rows_screen annb_gather_rows fused with the per-try preparation (fp16 copy and
+ *                           norms, written into the tail of `leaf_scratch`); pass the same
+ *                           scale_bits and rows_prepared = 1 to annb_leaf_topk afterwards      */
+int annb_screen_applies(size_t d, size_t d_short, size_t k);
+void annb_screen_scale(const ftype *points, const ftype *mean, size_t n, size_t d,
+                       unsigned *scale_bits, annb_stream stream);
+void annb_gather_rows_screen(const ftype *points, const annb_u32 *order, size_t n, size_t d,
+                             const ftype *mean, const unsigned *scale_bits, ftype *sorted_points,
+                             void *leaf_scratch, annb_stream stream);
 
 /* ---- S4: merge of the per-try lists (first sort_and_uniq of det_results, alg.c:312) ----
  * lists: [n_lists][n][k]; admit[i] = number of leading entries of list i that fall inside
