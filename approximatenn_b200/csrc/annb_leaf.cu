@@ -789,7 +789,7 @@ static void launch_screen(annb_stream stream, const FT *sp, const FT *mean, void
   if (grid > resident) grid = resident;
   u32 *ticket = flags.count + 32;
   RT_CHECK(cudaMemsetAsync(ticket, 0, sizeof(u32), stream));
-  leaf_screen_kernel<D><<<grid, 32, smem, stream>>>(sp, sp16, nrm, order, offset, tmax, n, buckets, d_short, k, ids, dist, flags, 0x8000000080000000ull, ticket, ct, ovf, getenv("ANN_B200_SCREEN_DBG") ? atoi(getenv("ANN_B200_SCREEN_DBG")) : 0);
+  leaf_screen_kernel<D><<<grid, 32, smem, stream>>>(sp, sp16, nrm, order, offset, tmax, n, buckets, d_short, k, ids, dist, flags, 0x8000000080000000ull, ticket, ct, ovf);
   LAUNCH_CHECK("leaf_screen");
   *ovf_out = ovf;
 }

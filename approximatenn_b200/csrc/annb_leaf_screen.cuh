@@ -5,26 +5,34 @@
 // approximation first and sends only the candidates whose bracket reaches the k-th best
 // through the exact tree (same operations, same order, same bits as the tiled kernel):
 //
-//   prep      once per try on the bucket-ordered copy: c = (x - mean) * scale (scale: a power
-//             of two that puts max|c| in [4, 8)), c' = fp16(c); sp16 row = c',
-//             nrm = (s, n2): s = sqrt(kappa) * (||c|| (1 + 2^-12) + sqrt(d) 2^-14), n2 = sum c'^2.
+//   scale     once per point set: a power of two that puts max |x - mean| in [4, 8).
+//   prep      once per try, fused with S2's gather: c = (x - mean) * scale, c' = fp16(c);
+//             sp16 row = c', nrm = (s, n2) with
+//             s = sqrt(kappa) * (||c|| (1 + 2^-12) + sqrt(d) 2^-14), n2 = sum c'^2.
 //   pass 1    16 queries of a bucket against the candidate stream, 8 candidates per
 //             mma.m16n8k16 (fp16 in, fp32 accumulate): D' = n2q + n2c - 2 q'.c'.  With
 //             t = sq + sc the exact-path value D (in scaled units) satisfies |D - D'| <= t^2
 //             (DESIGN.md "screened leaf": fp16 rounding of both rows incl. subnormals, the
-//             centring subtraction, the accumulation and the exact path's own rounding).
+//             centring subtraction, the accumulation and the exact path's own rounding;
+//             tests/test_screen_bounds.py checks the bracket on the CPU).
 //             lo = D' - t^2 is parked in shared memory as fp16 (rounded towards zero, negative
 //             values clamped to 0: still a lower bound); each lane keeps, per query and column
-//             parity, the 4 smallest upper bounds hi = D' + t^2 it has seen.  The four lanes
-//             that share a query then hold 32 upper bounds of 32 different candidates, and
-//             Theta = the 16th smallest of them is an upper bound of the 16th (hence k-th,
-//             k <= 16) smallest exact distance of the row.
-//   per query lo > Theta means strictly farther than the k-th best (not even a tie): dropped.
-//             The others (about k + a few) are evaluated exactly, 4 lanes per pair reading 64
-//             contiguous bytes per instruction, ranked by counting, and written out.
-// Buckets the screen cannot hold (more candidates than the shared-memory tables, or more than
-// 64 survivors for some query) are appended to a list and done by the tiled kernel afterwards,
-// so the result never depends on how well the screen did.
+//             parity, the 4 smallest upper bounds hi = D' + t^2 it has seen (as fp16, rounded
+//             to nearest: monotone, undone by a factor at the end).  The four lanes that share
+//             a query then hold 32 upper bounds of 32 different candidates, and Theta = the
+//             16th smallest of them bounds the 16th (hence k-th, k <= 16) smallest exact
+//             distance of the row from above.
+//   scan      lo > Theta means strictly farther than the k-th best (not even a tie): dropped.
+//             Lane (query, half of the stream) collects the others, about k + 2 per query.
+//   exact     the tile's (query, survivor) pairs as one flat list: 4 lanes per pair reading
+//             64 contiguous bytes per instruction, three rounds of 8 pairs in flight, query
+//             rows from shared memory (which reuses the parked-bounds area).
+//   rank      position = number of strictly smaller survivors of the same query; equal
+//             counts below k are exact ties and send the row to the literal kernel.
+// Buckets the screen cannot hold (more candidates than the shared-memory tables, more than 32
+// survivors in one half of a query's stream, or more than 512 pairs in a tile) are appended to
+// a list and done by the tiled kernel afterwards, so the result never depends on how well the
+// screen did.
 
 static __device__ unsigned long long leaf_exact_pairs_dev;   // pairs that reached the exact tree
 static __device__ unsigned long long leaf_overflow_dev;      // buckets handed to the tiled kernel
@@ -261,7 +269,7 @@ leaf_screen_kernel(const float *__restrict__ sp, const unsigned short *__restric
                    const u32 *__restrict__ offset, const u32 *__restrict__ tmax_p, size_t n,
                    size_t buckets, int d_short, int k, u32 *__restrict__ list_ids,
                    float *__restrict__ list_dist, TieList ties, unsigned long long negzero2,
-                   u32 *__restrict__ ticket, int CT, ScreenOverflow ovf, int dbg) {
+                   u32 *__restrict__ ticket, int CT, ScreenOverflow ovf) {
   constexpr int KS = D / 16;                                           // k-steps per candidate tile
   constexpr int NV = D / 16;                                           // 16-byte pieces per lane in the exact tree
   constexpr int QROW = ScreenOverlay<D>::QROW;
@@ -431,7 +439,6 @@ leaf_screen_kernel(const float *__restrict__ sp, const unsigned short *__restric
         if (t == 0) { theta[g] = th0; theta[g + 8] = th1; }
       }
       __syncwarp();
-      if (dbg == 1) continue;
 
       // ---- survivors of all 16 queries at once: lane = (query, half of the stream) -----
       const int sq = lane & 15, sh = lane >> 4;
@@ -465,7 +472,6 @@ leaf_screen_kernel(const float *__restrict__ sp, const unsigned short *__restric
       }
       __syncwarp();                                                     // lo_h is dead from here on
       if (overflow) break;
-      if (dbg == 2) continue;
 
       // ---- flat pair list of the tile (query-major, each query padded to 4) -------------
       // overlay on the parked bounds: query rows, distances, ids, pair tables
@@ -572,7 +578,6 @@ leaf_screen_kernel(const float *__restrict__ sp, const unsigned short *__restric
         if (lane == 0) atomicAdd(&leaf_exact_pairs_dev, (unsigned long long)Ptot);
       }
       __syncwarp();
-      if (dbg == 3) continue;
 
       // ---- ranks by counting: position = number of strictly smaller survivors of the same
       // query; two survivors with the same count are an exact tie, which matters below k ----

@@ -380,7 +380,10 @@ def main():
                           " (S3, summed over the tries of one step; includes prep and literal redo)",
                 "bound": "fp32", "achieved": leaf_tflops, "peak": fp32_peak,
                 "peak_source": "148 SM x 128 lanes x 1.965 GHz, one separately rounded FP32 op per lane-clock",
-                "unit": "TFLOP/s", "frac": leaf_tflops / fp32_peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": leaf_tflops / fp32_peak,
+                # DRAM read+write of ONE launch (one try) of leaf_screen_kernel<64> on this workload, from the
+                # committed ncu --set full capture (profiles/r1_q_ncu_leaf_screen_raw.csv); not re-measured here
+                "traffic": 839.5e6 if (screened and args.config == "cfg3" and world == 1) else None,
                 "pairs_per_step": leaf_pairs, "flops_per_pair": 3 * d,
                 "exact_pairs_per_step": exact_pairs, "screen_overflow_buckets_per_step": overflow_buckets,
                 "share_of_device_time": mean_stage["leaf"] / dev_mean}
