@@ -772,9 +772,10 @@ static void launch_screen(annb_stream stream, const FT *sp, const FT *mean, void
     screen_prep_kernel<<<grid_for(n * (D / 4), 256), 256, 0, stream>>>(sp, NULL, NULL, mean, n, D, scale_bits, sp16, nrm);
     LAUNCH_CHECK("screen_prep");
   }
-  // shared-memory tables sized for 1.25x the expected candidate count; bigger buckets go to the tiled kernel
+  // shared-memory tables sized a little above the expected candidate count (cfg3: 259 +- 16 -> 328);
+  // the few bigger buckets go to the tiled kernel, and the smaller footprint buys two more warps per SM
   double expect = (double)(d_short + 1) * ((double)n / (double)buckets);
-  size_t want = (size_t)(1.25 * expect) + 48;
+  size_t want = (size_t)(1.1 * expect) + 40;
   int ct = (int)(((want + 55) / 64) * 64 + 8);               // = 8 mod 64: conflict-free parking of the bounds
   if (ct > 1032) ct = 1032;
   if (ct < screen_min_ct(ScreenOverlay<D>::bytes)) ct = screen_min_ct(ScreenOverlay<D>::bytes);

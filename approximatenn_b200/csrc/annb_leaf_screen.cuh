@@ -30,7 +30,7 @@
 //   rank      position = number of strictly smaller survivors of the same query; equal
 //             counts below k are exact ties and send the row to the literal kernel.
 // Buckets the screen cannot hold (more candidates than the shared-memory tables, more than 32
-// survivors in one half of a query's stream, or more than 512 pairs in a tile) are appended to
+// survivors in one half of a query's stream, or more than 416 pairs in a tile) are appended to
 // a list and done by the tiled kernel afterwards, so the result never depends on how well the
 // screen did.
 
@@ -244,7 +244,7 @@ struct ScreenOverflow {
 
 static constexpr int SCREEN_HALF = 32;                 // survivor slots per (query, half of the stream)
 
-static constexpr int SCREEN_PAIRS = 512;               // (query, survivor) pairs per tile of 16 queries
+static constexpr int SCREEN_PAIRS = 416;               // (query, survivor) pairs per tile of 16 queries (cfg3: 300 +- 20)
 template <int D> struct ScreenOverlay {                // what replaces the parked bounds after the scan
   static constexpr int QROW = D + 4;                   // padded query row (floats)
   static constexpr size_t bytes = 16 * QROW * 4 + SCREEN_PAIRS * (4 + 4 + 2 + 2 + 1 + 1);
