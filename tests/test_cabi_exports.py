@@ -78,3 +78,31 @@ def test_save_t_layout_matches_header():
     # int tries; size_t n,k,d_short,d_long; size_t **which_par, *par_maxes, *graph; ftype *row_means, *bases
     assert ctypes.sizeof(SaveT) == 8 + 4 * 8 + 3 * 8 + 2 * 8
     assert SaveT.n.offset == 8 and SaveT.which_par.offset == 40 and SaveT.bases.offset == 72
+
+
+def test_screened_path_coverage_and_scratch_plan():
+    """Host-only entry points of the S3 stage: which shapes take the screened path, and that the
+    scratch plan grows by exactly the fp16 copy, the norms and the hand-over list when it does."""
+    from approximatenn_b200.api import gpu_backend
+    f32, f64 = gpu_backend(np.float32).lib, gpu_backend(np.float64).lib
+    for lib in (f32, f64):
+        lib.annb_screen_applies.argtypes = [ctypes.c_size_t] * 3
+        lib.annb_screen_applies.restype = ctypes.c_int
+        lib.annb_leaf_scratch_bytes.argtypes = [ctypes.c_size_t] * 4
+        lib.annb_leaf_scratch_bytes.restype = ctypes.c_size_t
+        lib.annb_leaf_screen_mode.argtypes = [ctypes.c_int]
+    try:
+        f32.annb_leaf_screen_mode(1)
+        assert [f32.annb_screen_applies(d, 16, 16) for d in (16, 32, 64, 128, 80)] == [1, 1, 1, 0, 0]
+        assert f32.annb_screen_applies(64, 16, 17) == 0            # k > 16: the tiled kernel
+        assert f32.annb_screen_applies(64, 0, 16) == 0             # a single bucket
+        assert f64.annb_screen_applies(64, 16, 16) == 0            # float only
+        f32.annb_leaf_screen_mode(0)
+        assert f32.annb_screen_applies(64, 16, 16) == 0
+    finally:
+        f32.annb_leaf_screen_mode(1)
+    n, d, ds = 1_000_000, 64, 16
+    plain = f32.annb_leaf_scratch_bytes(n, 128, ds, 16)            # shape the screen does not cover
+    extra = f32.annb_leaf_scratch_bytes(n, d, ds, 16) - plain
+    assert n * d * 2 + n * 8 + 4 * (1 << ds) <= extra <= n * d * 2 + n * 8 + 4 * (1 << ds) + 2048
+    assert f64.annb_leaf_scratch_bytes(n, d, ds, 16) == plain
