@@ -81,3 +81,69 @@ def test_duplicate_points_have_a_positive_slack():
     pairs = np.array([[i, i + 10] for i in range(150)])
     dprime, slack, exact = brackets(x, pairs)
     assert np.all(exact == 0) and np.all(slack > 0) and np.all(np.abs(dprime) <= slack)
+
+
+def _merge8(m):
+    """bitonic_merge8 of annb_leaf_screen.cuh: ascending sort of a bitonic sequence of 8."""
+    m = list(m)
+
+    def ce(a, b):
+        if m[a] > m[b]:
+            m[a], m[b] = m[b], m[a]
+    for i in range(4):
+        ce(i, i + 4)
+    for a, b in ((0, 2), (1, 3), (4, 6), (5, 7)):
+        ce(a, b)
+    for a, b in ((0, 1), (2, 3), (4, 5), (6, 7)):
+        ce(a, b)
+    return m
+
+
+def _quad_sixteenth_smallest(lists):
+    """quad_sixteenth_smallest: four lanes, each with two ascending lists of 4 (a, b)."""
+    m = [_merge8(list(a) + list(b)[::-1]) for a, b in lists]
+    c = []
+    for t in range(4):
+        other = m[t ^ 1]
+        vals = [(max if t & 1 else min)(m[t][i], other[7 - i]) for i in range(8)]
+        c.append(_merge8(vals))
+    w = []
+    for t in range(4):
+        other = c[t ^ 3]
+        w.append(max(min(c[t][r], other[7 - r]) for r in range(8)))
+    out = [max(w[t], w[t ^ 1]) for t in range(4)]
+    assert len(set(out)) == 1                       # every lane of the quad gets the same value
+    return out[0]
+
+
+def test_threshold_network_returns_the_sixteenth_smallest_of_32():
+    """The selection network behind Theta (an upper bound of the row's 16th smallest distance)."""
+    rng = np.random.default_rng(99)
+    for trial in range(2000):
+        vals = rng.standard_normal(32).astype(np.float32)
+        if trial % 5 == 0:
+            vals[rng.integers(0, 32, rng.integers(1, 24))] = np.inf     # rows with few candidates
+        if trial % 7 == 0:
+            vals[:8] = vals[8]                                          # repeated values
+        groups = vals.reshape(4, 2, 4)
+        lists = [(sorted(g[0]), sorted(g[1])) for g in groups]
+        assert _quad_sixteenth_smallest(lists) == np.sort(vals)[15]
+
+
+def test_keeping_four_per_lane_and_parity_bounds_the_sixteenth_smallest():
+    """Pass 1 keeps, per lane and column parity, the 4 smallest upper bounds it has seen; the
+    16th smallest of those 32 is never below the 16th smallest of the whole row."""
+    rng = np.random.default_rng(7)
+    for trial in range(300):
+        ncols = int(rng.integers(3, 60)) * 8
+        hi = rng.gamma(8.0, 1.0, ncols).astype(np.float32)
+        kept = []
+        for t in range(4):                          # lane t of the quad: columns j0 + 2t (+1)
+            for e in range(2):
+                col = hi[(np.arange(ncols) % 8) == 2 * t + e]
+                best = np.sort(np.concatenate([col, np.full(4, np.inf, np.float32)]))[:4]
+                kept.append(best)
+        lists = [(list(kept[2 * t]), list(kept[2 * t + 1])) for t in range(4)]
+        theta = _quad_sixteenth_smallest(lists)
+        truth = np.sort(np.concatenate([hi, np.full(16, np.inf, np.float32)]))[15]
+        assert theta >= truth
