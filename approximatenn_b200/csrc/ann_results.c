@@ -50,6 +50,7 @@ struct annh_egress {
   egress_arg arg[EGRESS_MAX_THREADS];
   pthread_mutex_t mu;
   pthread_cond_t cv;
+  pthread_barrier_t touched;   /* all pages faulted in before any result cell is written */
   int submitted, closed;
   egress_chunk chunk[EGRESS_MAX_CHUNKS];
 };
@@ -77,10 +78,11 @@ static void *egress_worker(void *p) {
   struct annh_egress *e = ((egress_arg *)p)->e;
   const int me = ((egress_arg *)p)->idx;
   cudaSetDevice(e->device);
-  /* 1. fault in this thread's share of the result pages while the GPU computes          */
+  /* 1. fault in this thread's share of the result pages while the GPU computes.  Shares are
+   *    whole rows; the barrier below keeps every zero written here ahead of every result
+   *    cell written in step 2 (a chunk may land while a slow thread is still touching).     */
   {
-    size_t cells = e->rows * e->k;
-    size_t lo = cells * (size_t)me / e->nthreads, hi = cells * (size_t)(me + 1) / e->nthreads;
+    size_t lo = (e->rows * (size_t)me / e->nthreads) * e->k, hi = (e->rows * (size_t)(me + 1) / e->nthreads) * e->k;
     volatile char *a = (volatile char *)(e->ids + lo);
     for (size_t o = 0; o < (hi - lo) * sizeof(size_t); o += 4096) a[o] = 0;
     if (hi > lo) a[(hi - lo) * sizeof(size_t) - 1] = 0;
@@ -95,6 +97,7 @@ static void *egress_worker(void *p) {
       if (hi > lo) b[(hi - lo) * sizeof(ftype) - 1] = 0;
     }
   }
+  pthread_barrier_wait(&e->touched);
   /* 2. every chunk, as it lands: this thread widens/copies its 1/nthreads share of the rows,
    *    so the tail after the last chunk is short                                            */
   for (int c = 0;; c++) {
@@ -155,6 +158,7 @@ annh_egress *annh_egress_begin(size_t rows, size_t k, int want_dist, int want_se
   if (nt < 1) nt = 1;
   if (nt > EGRESS_MAX_THREADS) nt = EGRESS_MAX_THREADS;
   e->nthreads = nt;
+  pthread_barrier_init(&e->touched, NULL, (unsigned)nt);
   for (int i = 0; i < nt; i++) {
     e->arg[i].e = e;
     e->arg[i].idx = i;
@@ -196,6 +200,7 @@ size_t *annh_egress_end(annh_egress *e, ftype **dists_o, size_t **second_ids_o) 
   for (int c = 0; c < e->submitted; c++) CK(cudaEventDestroy(e->chunk[c].done));
   pthread_mutex_destroy(&e->mu);
   pthread_cond_destroy(&e->cv);
+  pthread_barrier_destroy(&e->touched);
   size_t *ids = e->ids;
   if (dists_o) *dists_o = e->dist;
   if (second_ids_o) *second_ids_o = e->ids2;

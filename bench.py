@@ -10,12 +10,18 @@ config 3: n=1,000,000 d=64 k=16 float, 8 tries + supercharge, reference default 
 Printed JSON (one line, rank 0):
   value     points/s, device time only: inputs resident in HBM when the timed region starts
             (CUDA events on the library's stream, from after the upload to before the download)
-  e2e       points/s through the reference-facing C-ABI call precomp_gpu(host pointers):
-            pinned host input -> H2D -> all stages -> D2H into the malloc()ed result arrays
-  roofline  the dominant kernel against the measured peak (MEASURED_PEAKS.json)
+  e2e       points/s through the reference-facing C-ABI call precomp_gpu(host pointers), the
+            time_results protocol (time_results.c:90-129): malloc()ed (pageable) host input ->
+            H2D -> all stages -> D2H into the malloc()ed result arrays, free() of the results.
+            e2e.pinned repeats it with a page-locked input buffer.
+  roofline  the dominant kernel against measured peaks (MEASURED_PEAKS.json for HBM, the
+            library's own FFMA probe for the FP32 pipe)
+  parity_sample  the FINAL rows of sampled points, recomputed by the CPU oracle at full
+            problem size, compared bit for bit with the rows of the timed GPU runs
   cpu_baseline  the CPU restatement of the reference (oracle/, pinned bit-exact to the
-            reference's C path) timed on this box's host, 1 core, on a bounded sample
-`--impl reference` times that CPU path alone and prints the same line shape.
+            reference's C path) timed on this box's host, 1 core, on that bounded sample
+`--impl reference` times the reference's own C path (oracle/_ref, compiled from
+/root/reference) on the host and prints the same line shape.
 """
 from __future__ import annotations
 
@@ -53,6 +59,20 @@ def measured_peaks():
             j = json.load(f)
         return float(j["hbm_gbs"]), "measured"
     return 6650.0, "fallback"
+
+
+def committed_traffic(config, world):
+    """DRAM bytes (read + write) per launch of the hot kernels, from committed `ncu --set full`
+    captures of this workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py with
+    the commit it was captured on).  Nothing is assumed: no matching capture -> no number."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return {}
+    with open(p) as f:
+        j = json.load(f)
+    if j.get("config") != config or j.get("gpus", 1) != world:
+        return {}
+    return {k_: v for k_, v in j.get("kernels", {}).items()}
 
 
 def synth_points(n, d, dtype, seed=1):
@@ -119,25 +139,45 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.sm), "source": self.how}
 
 
+SEED = 1001                  # srandom() before every precomp: the transforms of the timed runs
+
+
+def sample_ids(n, count):
+    return np.sort(np.random.default_rng(99).choice(n, size=min(count, n), replace=False))
+
+
 def cpu_baseline(cfg, pts, sample_points):
-    """Reference algorithm on the host (1 core): bounded sample at full problem size."""
+    """Reference algorithm on the host (1 core): bounded sample at full problem size.  Returns
+    the baseline record and the exact final rows (ids, squared distances) of the sampled points
+    for the same seed as the timed GPU runs — the checker of `parity_sample`."""
     import oracle
     n, d, k, tries, dtype = cfg
     orc = oracle.restatement(dtype)
-    rng = np.random.default_rng(99)
-    sample = rng.choice(n, size=min(sample_points, n), replace=False)
+    sample = sample_ids(n, sample_points)
     from approximatenn_b200.api import srandom
-    srandom(4242)
+    srandom(SEED)
     t0 = time.time()
-    c = oracle.sampled_cost(orc, pts, k, tries, sample, *ROT)
+    ids, key, c = oracle.sampled_rows(orc, pts, k, tries, sample, *ROT)
     per_point = c["prepare_s"] / n + c["row_s"] + c["supercharge_s"]
-    return {"value": 1.0 / per_point, "unit": "points/s", "cores": 1, "kind": "port",
+    return (ids, key), {"value": 1.0 / per_point, "unit": "points/s", "cores": 1, "kind": "port",
             "sample": (f"oracle/ann_oracle.c (bit-exact restatement of the reference's precomp_cpu; the "
                        f"reference itself needs n*L*d*4 B = >100 GB of scratch at this size): hashing+tables "
                        f"for all {n} points, then per-try rows+merge for {c['rows']} points and supercharge "
                        f"for {len(sample)} sampled points; {time.time() - t0:.1f} s of CPU; points/s = "
                        f"1/(prepare/n + row + supercharge)"),
             "detail": {k_: float(v) for k_, v in c.items()}}
+
+
+def parity_sample(want, got_ids, got_d, sample):
+    """Bit-for-bit comparison of the oracle's rows with the GPU's rows of the same points."""
+    want_ids, want_d = want
+    same = (got_ids == want_ids).all(axis=1) & (
+        np.ascontiguousarray(got_d).view(np.uint8).reshape(len(sample), -1) ==
+        np.ascontiguousarray(want_d).view(np.uint8).reshape(len(sample), -1)).all(axis=1)
+    return {"rows": int(len(sample)), "mismatch": int((~same).sum()),
+            "compared": "final neighbour ids and squared distances (all bits) of the sampled points, oracle "
+                        "(oracle/ann_oracle.c, pinned to the reference) vs the rows returned by precomp_gpu",
+            "first_mismatching_points": [int(v) for v in sample[~same][:5]]}
 
 
 def measure_recall(gpu, pts, cfg, sample):
@@ -207,20 +247,76 @@ def measure_pair(gpu, pts, cfg, ycnt):
             "pair_ms": 1e3 * (tp + q1), "pair_points_plus_queries_per_s": (n + ycnt) / (tp + q1)}
 
 
+def reference_direct(name, n_override=None):
+    """The reference's own precomp_cpu (oracle/_ref, compiled unmodified from /root/reference) on a
+    BASELINE config, inputs from numpy's generator, time_results' clock placement
+    (time_results.c:121-129): wall time of the call including free() of the results."""
+    import oracle
+    from approximatenn_b200.api import srandom, _libc
+    n, d, k, tries, dtype = CONFIGS[name]
+    if n_override:
+        n = n_override
+    ref = oracle.reference(dtype)
+    pts = synth_points(n, d, dtype)
+    dptr = ctypes.c_void_p()
+    srandom(SEED)
+    t0 = time.perf_counter()
+    ids = ref.precomp_raw(n, k, d, pts.ctypes.data, tries, *ROT, None, ctypes.byref(dptr))
+    _libc.free(ids); _libc.free(dptr)
+    dt = time.perf_counter() - t0
+    ds = int(np.ceil(np.log2(np.float32(n) / np.float32(k)))) if dtype == np.float32 else int(np.ceil(np.log2(n / k)))
+    return {"config": name, "n": n, "d": d, "k": k, "tries": tries, "seconds": dt, "points_per_s": n / dt,
+            "d_short": min(ds, 1 << (d - 1).bit_length())}
+
+
+def expected_row_len(n, d_short, trials=3):
+    """L = (d_short+1)*tmax of the reference's candidate rows (alg.c:252-277) for uniformly hashed
+    points: tmax = largest of 2^d_short bucket counts (Monte Carlo, as SURVEY 8's table)."""
+    rng = np.random.default_rng(7)
+    tm = [np.bincount(rng.integers(0, 1 << d_short, size=n), minlength=1 << d_short).max() for _ in range(trials)]
+    return (d_short + 1) * float(np.median(tm))
+
+
 def run_reference_arm(args, cfg, name):
+    """--impl reference: the reference's OWN C path (oracle/_ref) on this box's host cores.  The
+    path is single-threaded by construction (ann.h:37-38), so cores = 1.  Configs the reference
+    can hold in memory (cfg1, cfg2) are timed directly, one call per step.  For cfg3-5 its scratch
+    buffer n*L*d*w (alg.c:237) exceeds any host, so each step times the reference on a bounded
+    problem of the same d, k, tries and the per-point cost is scaled by the ratio of candidate-row
+    lengths L (t ~ N*T*L*d) — labelled as extrapolated."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import oracle
     n, d, k, tries, dtype = cfg
-    pts = synth_points(n, d, dtype)
-    vals = []
+    if not oracle.reference_available():
+        line = {"impl": "reference", "unavailable": "oracle/_ref was not built (no /root/reference checkout when build() ran)"}
+        print(json.dumps(line), flush=True)
+        return
+    direct = name in ("cfg1", "cfg2")
+    n_run = n if direct else args.ref_sample_n
+    vals, runs = [], []
     for i in range(args.warmup + args.steps):
-        cb = cpu_baseline(cfg, pts, args.cpu_sample)
+        r = reference_direct(name, None if direct else n_run)
         if i >= args.warmup:
-            vals.append(cb)
-    v = statistics.mean(c["value"] for c in vals)
-    cb = vals[-1]
-    cb["value"] = v
+            runs.append(r)
+            vals.append(r["points_per_s"])
+    v_run = statistics.mean(vals)
+    scale, how = 1.0, "measured directly on the named config"
+    if not direct:
+        ds_full = int(np.ceil(np.log2(np.float32(n) / np.float32(k))))
+        L_full, L_run = expected_row_len(n, ds_full), expected_row_len(n_run, runs[-1]["d_short"])
+        scale = L_run / L_full
+        how = (f"EXTRAPOLATED: reference timed at n={n_run} (same d, k, tries), points/s scaled by the candidate-row "
+               f"length ratio L({n_run})/L({n}) = {L_run:.0f}/{L_full:.0f}; the reference itself cannot allocate its "
+               f"n*L*d*4 B scratch at n={n}")
+    v = v_run * scale
+    cb = {"value": v, "unit": "points/s", "cores": 1, "kind": "reference",
+          "sample": f"oracle/_ref precomp_cpu (the reference's C path, gcc -O2 -ffp-contract=off), {how}; "
+                    f"{len(runs)} timed call(s), mean {statistics.mean(r['seconds'] for r in runs):.2f} s each",
+          "measured_points_per_s_at_run_size": v_run, "run_n": n_run}
+    if args.ref_cfg1 and name != "cfg1":
+        cb["direct_cfg1"] = reference_direct("cfg1")          # BASELINE config 1, measured, never extrapolated
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "points/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * n / v, "higher_is_better": True, "scaling": "strong",
@@ -237,7 +333,9 @@ def workload_config(cfg, name, gpus):
                         f"rotations {ROT}, iid N(0,1) points",
             "n": n, "d": d, "k": k, "tries": tries, "gpus": gpus,
             "parallelism": "1 GPU" if gpus == 1 else f"tries sharded over {gpus} ranks, rows of merge+supercharge sliced, NCCL all-to-all/all-gather",
-            "l2": "inputs (n*d*4 B = %.0f MB) exceed the 126 MB L2; no flush needed" % (n * d * np.dtype(dtype).itemsize / 1e6)}
+            "l2": ("inputs (%.0f MB) plus the per-try lists (%.0f MB) exceed the 126 MB L2 and every step re-uploads "
+                   "the points; no flush between steps" % (n * d * np.dtype(dtype).itemsize / 1e6,
+                                                            n * k * tries * (4 + np.dtype(dtype).itemsize) / 1e6))}
 
 
 def main():
@@ -249,6 +347,12 @@ def main():
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--cpu-sample", type=int, default=256, help="points in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-sample", type=int, default=64,
+                    help="sampled points checked against the oracle when the CPU baseline does not run (N>1)")
+    ap.add_argument("--ref-sample-n", type=int, default=1024,
+                    help="--impl reference on cfg3-5: points of the bounded problem the reference is timed on")
+    ap.add_argument("--ref-cfg1", action="store_true",
+                    help="--impl reference: also time BASELINE config 1 directly (adds ~20-45 s)")
     ap.add_argument("--pair-queries", type=int, default=65536,
                     help="query vectors of the precomp(save)+query pair measurement (0 = skip)")
     ap.add_argument("--recall-sample", type=int, default=2000,
@@ -290,17 +394,21 @@ def main():
         from approximatenn_b200 import dist as adist
         adist.init_from_torch(gpu.lib, gather_full=False)
 
-    # pinned host input: the buffer the caller hands to precomp_gpu
+    # The caller's buffer, as the reference's time_results allocates it (time_results.c:90):
+    # plain malloc()ed, i.e. pageable, memory.  A page-locked copy is timed as an extra.
+    pts = synth_points(n, d, dtype)
     host = torch.empty((n, d), dtype=torch.float32 if dtype == np.float32 else torch.float64,
                        pin_memory=True)
-    pts = host.numpy()
-    pts[:] = synth_points(n, d, dtype)
+    pts_pinned = host.numpy()
+    pts_pinned[:] = pts
 
-    def step():
+    def step(src=pts, keep=None):
         dptr = ctypes.c_void_p()
-        srandom(1001)
-        ids = gpu.precomp_raw(n, k, d, pts.ctypes.data, tries, *ROT, None, ctypes.byref(dptr))
+        srandom(SEED)
+        ids = gpu.precomp_raw(n, k, d, src.ctypes.data, tries, *ROT, None, ctypes.byref(dptr))
         st = stage_times(gpu)
+        if keep is not None:
+            keep(ids, dptr)
         _libc.free(ids)
         _libc.free(dptr)
         return st
@@ -341,18 +449,60 @@ def main():
         step()
     barrier()
     wall = time.perf_counter() - t0
+    # timed region 3: page-locked caller buffer (extra)
+    step(pts_pinned)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(pts_pinned)
+    barrier()
+    wall_pinned = time.perf_counter() - t0
     gpu.lib.annh_set_timing(1)
     sampler.stop_flag.set()
     sampler.join()
+
+    # one more (untimed) run with the same seed whose rows are kept for the parity sample
+    run_baseline = world == 1 and not args.no_cpu_baseline
+    sample = sample_ids(n, args.cpu_sample if run_baseline else args.parity_sample)
+    lo, hi = 0, n
+    if world > 1:
+        from approximatenn_b200 import dist as adist
+        lo, hi = adist.row_slice(gpu.lib, n, rank, world)
+    mine = sample[(sample >= lo) & (sample < hi)]
+    kept = {}
+
+    def keep_rows(ids_p, d_p):
+        from approximatenn_b200.api import _view
+        kept["ids"] = _view(ids_p, (hi - lo, k), np.uint64)[mine - lo].copy()
+        kept["d"] = _view(d_p, (hi - lo, k), dtype)[mine - lo].copy()
+
+    step(pts, keep_rows)
 
     dev_keys = ("means", "hash", "buckets", "leaf", "exchange", "merge", "supercharge")
     dev_ms = [sum(s[k_] for k_ in dev_keys) for s in stages]
     dev_total_s = sum(dev_ms) / 1e3
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([dev_total_s, wall], device="cuda", dtype=torch.float64)
+        t = torch.tensor([dev_total_s, wall, wall_pinned], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_total_s, wall = float(t[0]), float(t[1])
+        dev_total_s, wall, wall_pinned = float(t[0]), float(t[1]), float(t[2])
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object((mine, kept["ids"], kept["d"]), parts, dst=0)
+        stage_all = [None] * world if rank == 0 else None
+        dist.gather_object({k_: statistics.mean(s[k_] for s in stages) for k_ in stages[0]}, stage_all, dst=0)
+        if rank == 0:
+            mine = np.concatenate([p_[0] for p_ in parts])
+            kept = {"ids": np.concatenate([p_[1] for p_ in parts]), "d": np.concatenate([p_[2] for p_ in parts])}
+            o = np.argsort(mine, kind="stable")
+            mine, kept = mine[o], {"ids": kept["ids"][o], "d": kept["d"][o]}
+    fp32_probe = None
+    if rank == 0:
+        gpu.lib.annb_probe_fp32.restype = ctypes.c_double
+        gpu.lib.annb_probe_fp32.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        gpu.lib.annh_stream.restype = ctypes.c_void_p
+        st_ = gpu.lib.annh_stream()
+        fp32_probe = {m_: float(gpu.lib.annb_probe_fp32(i_, 3, st_)) for i_, m_ in
+                      enumerate(("ffma", "fmul_fadd", "ffma2", "fmul2_fadd2"))}
     if world > 1:
         gpu.lib.annb200_dist_shutdown()
         dist.barrier()
@@ -366,24 +516,26 @@ def main():
     dev_mean = statistics.mean(dev_ms)
     # --- dominant kernel: S3 (leaf_screen_kernel, or leaf_topk_tile_kernel where the screen does
     # not apply).  Algorithmic work per (point, candidate) pair = d subtractions + d multiplications
-    # + d-1 additions, each rounded separately (the reference's arithmetic, compute.cl:147-166; an
-    # FMA would change its bits), counted as 3*d flops.  Peak = one rounded FP32
-    # operation per lane per clock: 148 SMs x 128 lanes x max SM clock (half of the usual
-    # FFMA-counts-two figure).  The screened kernel reaches its rate by NOT executing most of these
-    # flops: fp16 tensor-core brackets leave `exact_pairs_per_step` pairs for the exact tree, so
-    # `frac` is algorithmic work over peak, not pipe utilisation (ncu: profiles/).
+    # + d-1 additions (compute.cl:147-166), counted as 3*d flops.  `peak` is the FP32
+    # pipe measured by the library's own probe (annb_probe.cu) as FFMA chains, an FMA counting two
+    # flops (the SURVEY 8.D convention); `frac_separately_rounded` divides by the measured rate of
+    # packed, separately rounded FMUL2+FADD2 chains instead — the only form the reference's bits
+    # allow (an FMA would change them).  The screened kernel reaches its rate by NOT executing most
+    # of these flops: fp16 tensor-core brackets leave `exact_pairs_per_step` pairs for the exact
+    # tree, so `frac` is algorithmic work over peak, not pipe utilisation (ncu: profiles/).
+    traffic = committed_traffic(args.config, world)
     leaf_s = mean_stage["leaf"] / 1e3
-    fp32_peak = 148 * 128 * 1.965e9 / 1e12
+    fp32_peak = fp32_probe["ffma"]
     leaf_tflops = 3 * d * leaf_pairs / leaf_s / 1e12 if leaf_s > 0 else 0.0
     screened = exact_pairs > 0
-    roofline = {"kernel": ("leaf_screen_kernel" if screened else "leaf_topk_tile_kernel") +
-                          " (S3, summed over the tries of one step; includes prep and literal redo)",
+    leaf_kernel = "leaf_screen_kernel" if screened else "leaf_topk_tile_kernel"
+    roofline = {"kernel": leaf_kernel + " (S3, summed over the tries of one step; includes prep and literal redo)",
                 "bound": "fp32", "achieved": leaf_tflops, "peak": fp32_peak,
-                "peak_source": "148 SM x 128 lanes x 1.965 GHz, one separately rounded FP32 op per lane-clock",
-                "unit": "TFLOP/s", "frac": leaf_tflops / fp32_peak,
-                # DRAM read+write of ONE launch (one try) of leaf_screen_kernel<64> on this workload, from the
-                # committed ncu --set full capture (profiles/r1_q_ncu_leaf_screen_raw.csv); not re-measured here
-                "traffic": 839.5e6 if (screened and args.config == "cfg3" and world == 1) else None,
+                "peak_source": "annb_probe_fp32: FFMA chains on this device, FMA = 2 flops (measured live)",
+                "unit": "TFLOP/s", "frac": leaf_tflops / fp32_peak if fp32_peak else None,
+                "frac_separately_rounded": leaf_tflops / fp32_probe["fmul2_fadd2"] if fp32_probe["fmul2_fadd2"] else None,
+                "fp32_probe_tflops": fp32_probe,
+                "traffic": traffic.get(leaf_kernel),
                 "pairs_per_step": leaf_pairs, "flops_per_pair": 3 * d,
                 "exact_pairs_per_step": exact_pairs, "screen_overflow_buckets_per_step": overflow_buckets,
                 "share_of_device_time": mean_stage["leaf"] / dev_mean}
@@ -393,10 +545,21 @@ def main():
     rows = n / world                      # supercharge rows per rank
     sc_bytes = rows * (P2 - k) * (4 + d * w) + rows * k * (4 + w) + rows * k * (4 + w)
     sc_s = mean_stage["supercharge"] / 1e3
-    roofline_hbm = {"kernel": "supercharge_fast_kernel (S5, all row chunks of one step)", "bound": "hbm",
+    roofline_hbm = {"kernel": "supercharge kernels (S5, all row chunks of one step)", "bound": "hbm",
                     "achieved": sc_bytes / sc_s / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": sc_bytes / sc_s / 1e9 / peak, "traffic": None,
+                    "frac": sc_bytes / sc_s / 1e9 / peak, "traffic": traffic.get("supercharge"),
                     "share_of_device_time": mean_stage["supercharge"] / dev_mean}
+    # --- the whole step against HBM (SURVEY 8.D's per-run byte model; w = sizeof ftype, B = buckets)
+    ds = int(np.ceil(np.log2((np.float32(n) if dtype == np.float32 else np.float64(n)) / k)))
+    ds = min(ds, 1 << (d - 1).bit_length())
+    B = 1 << ds
+    step_bytes = (n * d * w) + (n * d * w + 4 * n * tries) + tries * (12 * n + 8 * B) + \
+        tries * (n * d * w + n * k * (4 + w)) + (n * k * tries * (4 + w) + n * k * (4 + w)) + \
+        (n * (P2 - k) * (4 + d * w) + n * k * (4 + w) + n * k * (8 + w))
+    step_s = dev_total_s / args.steps
+    roofline_step = {"what": "all stages of one step, SURVEY 8.D algorithmic bytes / device time (all ranks)",
+                     "bound": "hbm", "algorithmic_bytes": step_bytes, "achieved": step_bytes / step_s / 1e9,
+                     "peak": peak * world, "unit": "GB/s", "frac": step_bytes / step_s / 1e9 / (peak * world)}
     line = {"metric": METRIC, "value": n * args.steps / dev_total_s, "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_total_s / args.steps, "higher_is_better": True,
@@ -406,15 +569,27 @@ def main():
             "e2e": {"value": n * args.steps / wall, "unit": "points/s",
                     "h2d_bytes_per_step": n * d * w, "d2h_bytes_per_step": n * k * (4 + w),
                     "ms_per_step": 1e3 * wall / args.steps,
-                    "ms_per_step_with_stage_events": 1e3 * wall_instrumented / args.steps},
+                    "input": "malloc()ed (pageable) host array, the time_results protocol",
+                    "ms_per_step_with_stage_events": 1e3 * wall_instrumented / args.steps,
+                    "pinned": {"value": n * args.steps / wall_pinned, "ms_per_step": 1e3 * wall_pinned / args.steps,
+                               "input": "page-locked host array"}},
             "gpu_launches": launches, "stage_ms": mean_stage, "roofline": roofline, "roofline_hbm": roofline_hbm,
-            "clocks": sampler.summary()}
+            "roofline_step": roofline_step, "clocks": sampler.summary(), "host_cores": os.cpu_count()}
+    if world > 1:
+        line["stage_ms_per_rank"] = stage_all
     if args.recall_sample > 0 and world == 1:
         line["recall"] = measure_recall(gpu, pts, cfg, args.recall_sample)
     if args.pair_queries > 0 and world == 1:
         line["precomp_query_pair"] = measure_pair(gpu, pts, cfg, args.pair_queries)
-    if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(cfg, pts, args.cpu_sample)
+    if run_baseline:
+        want, line["cpu_baseline"] = cpu_baseline(cfg, pts, args.cpu_sample)
+    else:
+        import oracle
+        srandom(SEED)
+        ids_, key_, _ = oracle.sampled_rows(oracle.restatement(dtype), pts, k, tries, sample, *ROT)
+        want = (ids_, key_)
+    assert np.array_equal(mine, sample), "every sampled point must be owned by exactly one rank"
+    line["parity_sample"] = parity_sample(want, kept["ids"], kept["d"], sample)
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)

@@ -183,6 +183,13 @@ void annb_leaf_screen_mode(int on);
 /* rows redone by the literal kernels since the last reset: [0] S3, [1] S4, [2] S5 (synchronous)  */
 void annb_literal_rows(unsigned long long out[3], int reset);
 
+/* FP32-pipe probe (annb_probe.cu): TFLOP/s of dependent-chain streams of
+ *   mode 0 FFMA (2 flops/instruction)   1 FMUL+FADD (separately rounded, 1 flop/instruction)
+ *   mode 2 FFMA2 (packed, 4 flops)      3 FMUL2+FADD2 (packed, separately rounded, 2 flops)
+ * best of `reps` launches, timed with CUDA events on `stream` (synchronous).  These are the
+ * measured denominators of the S3 roofline (SURVEY 8.D asks for a measured FP32 figure).       */
+double annb_probe_fp32(int mode, int reps, annb_stream stream);
+
 /* number of kernels launched through this layer since the last reset (bench.py reports it) */
 unsigned long annb_launch_count(int reset);
 

@@ -85,6 +85,9 @@ def _declare_stage_api(b: Backend) -> None:
     L.orc_sampled_cost.argtypes = [sz, sz, sz, vp, ctypes.c_int, sz, sz, sz, sz, vp, sz,
                                    ctypes.POINTER(ctypes.c_double)]
     L.orc_sampled_cost.restype = sz
+    L.orc_sampled_rows.argtypes = [sz, sz, sz, vp, ctypes.c_int, sz, sz, sz, sz, vp, sz,
+                                   ctypes.POINTER(ctypes.c_double), vp, vp]
+    L.orc_sampled_rows.restype = sz
 
 
 def params(b: Backend, n, k, d):
@@ -163,6 +166,21 @@ def sampled_cost(b: Backend, points, k, tries, sample, rots_before=6, rot_len_be
                                   rots_before, rot_len_before, rots_after, rot_len_after,
                                   sample.ctypes.data, len(sample), secs)
     return {"prepare_s": secs[0], "row_s": secs[1], "supercharge_s": secs[2], "rows": rows}
+
+
+def sampled_rows(b: Backend, points, k, tries, sample, rots_before=6, rot_len_before=1,
+                 rots_after=1, rot_len_after=1):
+    """Exact final rows (after supercharging) of the `sample` points of a full-size problem,
+    plus the timings of sampled_cost().  Seed libc random() first (api.srandom)."""
+    pts = np.ascontiguousarray(points, dtype=b.dtype)
+    sample = np.ascontiguousarray(sample, dtype=np.uint64)
+    secs = (ctypes.c_double * 3)()
+    ids = np.empty((len(sample), k), dtype=np.uint64)
+    key = np.empty((len(sample), k), dtype=b.dtype)
+    rows = b.lib.orc_sampled_rows(pts.shape[0], k, pts.shape[1], pts.ctypes.data, tries,
+                                  rots_before, rot_len_before, rots_after, rot_len_after,
+                                  sample.ctypes.data, len(sample), secs, ids.ctypes.data, key.ctypes.data)
+    return ids, key, {"prepare_s": secs[0], "row_s": secs[1], "supercharge_s": secs[2], "rows": rows}
 
 
 def merge_rows(b: Backend, ids, key):

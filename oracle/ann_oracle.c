@@ -574,9 +574,10 @@ void free_save_oracle(save_t *save) {                      /* ann.c:25-34 */
  * supercharging step reads, then supercharging of the sampled points.
  * secs[0] = hashing+tables for all n, secs[1] = per-try rows+merge per processed row,
  * secs[2] = supercharging per sampled point.  Returns the number of rows processed.       */
-size_t orc_sampled_cost(size_t n, size_t k, size_t d, const ftype *points, int tries,
-                        size_t rots_b, size_t len_b, size_t rots_a, size_t len_a,
-                        const size_t *sample, size_t m, double secs[3]) {
+static size_t sampled_impl(size_t n, size_t k, size_t d, const ftype *points, int tries,
+                           size_t rots_b, size_t len_b, size_t rots_a, size_t len_a,
+                           const size_t *sample, size_t m, double secs[3], size_t *out_ids,
+                           ftype *out_key) {
   struct timespec t0, t1;
   clock_gettime(CLOCK_MONOTONIC, &t0);
   orc_state *s = orc_prepare(n, k, d, points, tries, rots_b, len_b, rots_a, len_a);
@@ -629,6 +630,8 @@ size_t orc_sampled_cost(size_t n, size_t k, size_t d, const ftype *points, int t
     }
     row_distances(&w, k, wide, points + sample[i] * d, sample[i], points, n, d);
     sort_and_uniq_row(w.ids, w.key, wide);
+    if (out_ids) memcpy(out_ids + i * k, w.ids, sizeof(size_t) * k);
+    if (out_key) memcpy(out_key + i * k, w.key, sizeof(ftype) * k);
   }
   clock_gettime(CLOCK_MONOTONIC, &t1);
   secs[2] = ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec)) / (double)m;
@@ -637,6 +640,22 @@ size_t orc_sampled_cost(size_t n, size_t k, size_t d, const ftype *points, int t
   free(ids_k); free(key_k); free(row_of); free(ids); free(key);
   orc_release(s, 0);
   return rows;
+}
+
+size_t orc_sampled_cost(size_t n, size_t k, size_t d, const ftype *points, int tries,
+                        size_t rots_b, size_t len_b, size_t rots_a, size_t len_a,
+                        const size_t *sample, size_t m, double secs[3]) {
+  return sampled_impl(n, k, d, points, tries, rots_b, len_b, rots_a, len_a, sample, m, secs, NULL, NULL);
+}
+
+/* Same walk, but the FINAL rows (ids and squared distances after supercharging, alg.c:328-335)
+ * of the sampled points are returned: exact parity rows at sizes where a full run of the
+ * restatement would take hours.  out_ids/out_key: [m][k].                                   */
+size_t orc_sampled_rows(size_t n, size_t k, size_t d, const ftype *points, int tries,
+                        size_t rots_b, size_t len_b, size_t rots_a, size_t len_a,
+                        const size_t *sample, size_t m, double secs[3], size_t *out_ids,
+                        ftype *out_key) {
+  return sampled_impl(n, k, d, points, tries, rots_b, len_b, rots_a, len_a, sample, m, secs, out_ids, out_key);
 }
 
 /* ------------------------------------------------------------------------------------ */

@@ -35,6 +35,30 @@ def run_case(gpu, dtype, n, d, k, tries, seed, gather):
     return ok
 
 
+def run_sampled_case(gpu, dtype, n, d, k, tries, seed, samples):
+    """Full-size problem (the oracle cannot run all of it in test time): every rank checks the
+    sampled points that fall into its row slice against the oracle's exact final rows."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rng = np.random.default_rng(seed)
+    pts = rng.standard_normal((n, d), dtype=np.float32).astype(dtype)
+    gpu.lib.annb200_dist_gather(0)
+    lo, hi = adist.row_slice(gpu.lib, n, rank, world)
+    sample = np.sort(rng.choice(n, size=samples, replace=False))
+    mine = sample[(sample >= lo) & (sample < hi)]
+    dptr = ctypes.c_void_p()
+    srandom(seed)
+    ids = gpu.precomp_raw(n, k, d, pts.ctypes.data, tries, 6, 1, 1, 1, None, ctypes.byref(dptr))
+    got_ids = _view(ids, (hi - lo, k), np.uint64)[mine - lo].copy()
+    got_d = _view(dptr, (hi - lo, k), dtype)[mine - lo].copy()
+    _libc.free(ids); _libc.free(dptr)
+    srandom(seed)
+    want_ids, want_d, _ = oracle.sampled_rows(oracle.restatement(dtype), pts, k, tries, mine)
+    ok = np.array_equal(got_ids, want_ids) and np.array_equal(got_d.view(np.uint8), want_d.view(np.uint8))
+    print(f"rank {rank}/{world} {np.dtype(dtype).name} n={n} d={d} k={k} T={tries} sampled rows "
+          f"{len(mine)} of [{lo},{hi}) {'OK' if ok else 'MISMATCH'}", flush=True)
+    return ok
+
+
 def run_save_case(gpu, dtype, n, d, k, tries, seed):
     """save != NULL in sharded mode: every rank ends up with the complete index."""
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -73,9 +97,14 @@ def main():
         (np.float32, 5003, 16, 10, 10, 402, False),     # k*T = 100: prefix corner, uneven try split
         (np.float64, 4096, 32, 16, 5, 403, False),      # more ranks than some ranks have tries
         (np.float32, 3000, 20, 10, 3, 404, True),
+        (np.float32, 8191, 64, 16, 5, 407, False),      # T = 5: ranks 5.. own no try at 8 ranks; odd n
+        (np.float32, 2049, 32, 8, 8, 408, False),       # ceil(n/R) rounds up to 32 rows: short or empty last slice
+        (np.float64, 6007, 16, 10, 10, 409, True),      # double, prefix corner, n prime
+        (np.float32, 224, 16, 4, 4, 411, False),        # 8 ranks: slices of 32 rows, the last one is empty
     ]
     for dtype, n, d, k, tries, seed, gather in cases:
         ok &= run_case(gpus[dtype], dtype, n, d, k, tries, seed, gather)
+    ok &= run_sampled_case(gpus[np.float32], np.float32, 1_000_000, 64, 16, 8, 410, 96)   # BASELINE config 3
     ok &= run_save_case(gpus[np.float32], np.float32, 6000, 32, 16, 5, 405)
     ok &= run_save_case(gpus[np.float64], np.float64, 3000, 20, 10, 4, 406)
     flag = torch.tensor([1 if ok else 0], device="cuda")
