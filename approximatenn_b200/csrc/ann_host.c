@@ -408,6 +408,8 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
                  pad256(Tl * d_max * 4 + 4) + pad256(Tl * d_short * 4 + 4) +
                  pad256(annb_hash_scratch_bytes(&desc)) +
                  pad256(scratch_bytes) + 8192 + 256;
+  const int s5_screened = annb_supercharge_screen_applies(d, k);
+  if (s5_screened) fixed += pad256(n * d * 2);                /* fp16 copy of the points, original order */
   if (sharded && save) fixed += pad256(T * n * 4);            /* every try's hashes, for the tables */
   if (sharded)   /* merged ids (all rows), merged dists + results (own rows), exchanged lists */
     fixed += pad256(np * k * 4) + pad256(my_rows * k * w) + pad256(my_rows * k * 4) + pad256(my_rows * k * w) +
@@ -453,6 +455,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   int *dstatus = annh_arena_take(sizeof(int));
   unsigned *dscreen = annh_arena_take(256);                     /* scale word of the screened S3 path */
   const int screened = annb_screen_applies(d, d_short, k);
+  void *dX16 = s5_screened ? annh_arena_take(n * d * 2) : NULL;
   annb_u32 *dhash_all = (sharded && save) ? annh_arena_take(T * n * 4) : NULL;
   annb_u32 *ds_ids = sharded ? annh_arena_take(T * my_rows * k * 4) : NULL;   /* [T][my_rows][k] */
   ftype *ds_dist = sharded ? annh_arena_take(T * my_rows * k * w) : NULL;
@@ -489,7 +492,8 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
     }
   }
   annb_scale_means(dXs, n, d, dmean, st);
-  if (screened && Tl) annb_screen_scale(dX, dmean, n, d, dscreen, st);
+  if ((screened && Tl) || s5_screened) annb_screen_scale(dX, dmean, n, d, dscreen, st);
+  if (s5_screened) annb_screen_prep_points(dX, dmean, n, d, dscreen, dX16, st);
 
   /* 5. S1 hashes of every owned try in one pass over the points                         */
   span_end(sp);
@@ -592,6 +596,8 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
 
   /* 7. S5 supercharging of the owned rows (alg.c:313-327); graph = the merged lists        */
   {
+    annb_supercharge_opts s5;
+    s5.points16 = dX16; s5.scale_bits = dscreen; s5.row_perm = NULL;
     int nch = full_result && sharded ? 1 : annh_egress_chunks(eg);
     for (int c = 0; c < nch; c++) {
       size_t r0 = row_lo + ((my_rows * (size_t)c / nch) & ~(size_t)31);
@@ -599,7 +605,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
       sp = span_begin(7);
       annb_supercharge(dX, dX, dm_ids, own_dist_base, dm_ids, n, d, k, r0, r1, 1,
                        dout_ids + (r0 - out_base) * k, dout_dist + (r0 - out_base) * k, dscratch,
-                       scratch_bytes, dstatus, st);
+                       scratch_bytes, dstatus, s5_screened ? &s5 : NULL, st);
       span_end(sp);
       if (!(full_result && sharded))
         annh_egress_chunk(eg, r0 - row_lo, r1 - row_lo, dout_ids + (r0 - out_base) * k,

@@ -3,7 +3,7 @@
  * The API takes plain host pointers (ann.h); the reference's callers malloc() them, i.e. the
  * memory is pageable and a single cudaMemcpy moves it at the speed of ONE thread copying into
  * the driver's bounce buffer (~11 GB/s measured: 23 ms for the 256 MB of cfg3, more than half of
- * the whole GPU computation).  Here a few host threads copy chunks into a ring of pinned
+ * the whole GPU computation).  Here several host threads copy chunks into a ring of pinned
  * staging slots and each chunk goes out by DMA as soon as it is staged, so the copy runs at the
  * memory bandwidth of several cores and overlaps with the DMA.  Pinned (or registered) input
  * is recognised and sent with one cudaMemcpyAsync as before.
@@ -27,35 +27,50 @@
     }                                                                                   \
   } while (0)
 
-#define INGEST_THREADS 4
-#define INGEST_SLOTS 8                       /* two per thread                            */
-#define INGEST_CHUNK ((size_t)8 << 20)       /* bytes per slot                            */
+#define INGEST_MAX_THREADS 16
+#define INGEST_PER_THREAD 2                  /* staging slots per thread                   */
+#define INGEST_SLOTS (INGEST_MAX_THREADS * INGEST_PER_THREAD)
+#define INGEST_CHUNK ((size_t)4 << 20)       /* bytes per slot                            */
 
 static struct {
   char *ring;                                /* INGEST_SLOTS * INGEST_CHUNK pinned bytes   */
-  cudaStream_t stream[INGEST_THREADS];
+  cudaStream_t stream[INGEST_MAX_THREADS];
   cudaEvent_t slot_free[INGEST_SLOTS];
-  cudaEvent_t done[INGEST_THREADS];
+  cudaEvent_t done[INGEST_MAX_THREADS];
   int ready;
 } I;
 
 void annh_ingest_release(void) {
   if (!I.ready) return;
-  for (int i = 0; i < INGEST_THREADS; i++) { cudaStreamDestroy(I.stream[i]); cudaEventDestroy(I.done[i]); }
+  for (int i = 0; i < INGEST_MAX_THREADS; i++) { cudaStreamDestroy(I.stream[i]); cudaEventDestroy(I.done[i]); }
   for (int i = 0; i < INGEST_SLOTS; i++) cudaEventDestroy(I.slot_free[i]);
   cudaFreeHost(I.ring);
   memset(&I, 0, sizeof I);
 }
 
-typedef struct { const char *src; char *dst; size_t bytes; int me, device; } ingest_job;
+typedef struct { const char *src; char *dst; size_t bytes; int me, device, threads; } ingest_job;
+
+/* One memcpy thread moves ~6-8 GB/s into the pinned ring and PCIe 5 takes ~54 GB/s, so the
+ * copy needs about eight of them; the count follows the cores the box has (the egress
+ * threads are only touching pages at this point of the call).                               */
+static int ingest_threads(void) {
+  int nt = 8;
+  const char *env = getenv("ANN_B200_INGEST_THREADS");
+  if (env && *env) nt = atoi(env);
+  long cores = sysconf(_SC_NPROCESSORS_ONLN);
+  if (cores > 2 && nt > cores - 2) nt = (int)cores - 2;
+  if (nt < 1) nt = 1;
+  if (nt > INGEST_MAX_THREADS) nt = INGEST_MAX_THREADS;
+  return nt;
+}
 
 static void *ingest_worker(void *p) {
   ingest_job *j = p;
   cudaSetDevice(j->device);
   size_t chunks = (j->bytes + INGEST_CHUNK - 1) / INGEST_CHUNK;
   int use = 0;
-  for (size_t c = j->me; c < chunks; c += INGEST_THREADS, use++) {
-    int slot = j->me * (INGEST_SLOTS / INGEST_THREADS) + (use % (INGEST_SLOTS / INGEST_THREADS));
+  for (size_t c = j->me; c < chunks; c += j->threads, use++) {
+    int slot = j->me * INGEST_PER_THREAD + (use % INGEST_PER_THREAD);
     size_t off = c * INGEST_CHUNK, len = j->bytes - off < INGEST_CHUNK ? j->bytes - off : INGEST_CHUNK;
     char *stage = I.ring + (size_t)slot * INGEST_CHUNK;
     if (cudaEventSynchronize(I.slot_free[slot]) != cudaSuccess) exit(1);   /* DMA of its last use done */
@@ -88,7 +103,7 @@ void annh_ingest(void *dst, const void *src, size_t bytes, void *consumer, int d
   }
   if (!I.ready) {
     CK(cudaMallocHost((void **)&I.ring, (size_t)INGEST_SLOTS * INGEST_CHUNK));
-    for (int i = 0; i < INGEST_THREADS; i++) {
+    for (int i = 0; i < INGEST_MAX_THREADS; i++) {
       CK(cudaStreamCreateWithFlags(&I.stream[i], cudaStreamNonBlocking));
       CK(cudaEventCreateWithFlags(&I.done[i], cudaEventDisableTiming));
     }
@@ -96,13 +111,15 @@ void annh_ingest(void *dst, const void *src, size_t bytes, void *consumer, int d
       CK(cudaEventCreateWithFlags(&I.slot_free[i], cudaEventDisableTiming | cudaEventBlockingSync));
     I.ready = 1;
   }
-  pthread_t th[INGEST_THREADS];
-  ingest_job job[INGEST_THREADS];
-  for (int i = 0; i < INGEST_THREADS; i++) {
+  const int nt = ingest_threads();
+  pthread_t th[INGEST_MAX_THREADS];
+  ingest_job job[INGEST_MAX_THREADS];
+  for (int i = 0; i < nt; i++) {
     job[i].src = src; job[i].dst = dst; job[i].bytes = bytes; job[i].me = i; job[i].device = device;
+    job[i].threads = nt;
     if (pthread_create(&th[i], NULL, ingest_worker, &job[i]) != 0) annh_fatal("%s", "pthread_create failed");
   }
-  for (int i = 0; i < INGEST_THREADS; i++) {
+  for (int i = 0; i < nt; i++) {
     pthread_join(th[i], NULL);
     CK(cudaStreamWaitEvent(st, I.done[i], 0));
   }

@@ -261,7 +261,7 @@ size_t *query_gpu(const save_t *save, const ftype *points, size_t ycnt, const ft
     size_t r1 = c + 1 == nch ? ycnt : (ycnt * (size_t)(c + 1) / nch) & ~(size_t)31;
     annb_supercharge(dq, IDX.d_points, down_ids, down_dist, IDX.d_graph, n, d, k, r0, r1, same_set,
                      dout_ids + r0 * k, dists_o ? dout_dist + r0 * k : NULL, dscratch, scratch_bytes,
-                     dstatus, st);
+                     dstatus, NULL, st);
     annh_egress_chunk(eg, r0, r1, dout_ids + r0 * k, dout_dist + r0 * k, st);
   }
   int h_status = 0;

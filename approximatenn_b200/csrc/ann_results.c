@@ -149,10 +149,10 @@ annh_egress *annh_egress_begin(size_t rows, size_t k, int want_dist, int want_se
   e->stage_ids = (annb_u32 *)((char *)S.stage + ((rows * k * sizeof(ftype) + 255) & ~(size_t)255));
   pthread_mutex_init(&e->mu, NULL);
   pthread_cond_init(&e->cv, NULL);
-  int nt = 4;
+  long cores = sysconf(_SC_NPROCESSORS_ONLN);
+  int nt = cores >= 12 ? 6 : 4;
   const char *env = getenv("ANN_B200_HOST_THREADS");
   if (env && *env) nt = atoi(env);
-  long cores = sysconf(_SC_NPROCESSORS_ONLN);
   if (cores > 1 && nt > cores - 1) nt = (int)cores - 1;
   if (rows * k < ((size_t)1 << 18)) nt = 1;
   if (nt < 1) nt = 1;

@@ -37,6 +37,10 @@ void annb_finish_literal_counts(unsigned long long out[2], int reset);
     }                                                                                   \
   } while (0)
 
+// sqrt(kappa) of the fp16 distance brackets shared by the screened S3 and S5 kernels
+// (kappa = 0.00104, DESIGN.md "screened leaf")
+static constexpr float SCREEN_SQRT_KAPPA = 0.03226f;
+
 static inline void fatal_config(const char *what) {
   fprintf(stderr, "approximatenn_b200: unsupported configuration: %s\n", what);
   exit(1);

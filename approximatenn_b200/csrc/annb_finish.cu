@@ -188,6 +188,139 @@ merge_lists_fast_kernel(const u32 *__restrict__ lists_ids, const FT *__restrict_
   if (tie && ties.rows && lane == 0) tie_report(ties, (u32)x);
 }
 
+// One THREAD per point (any k, up to ML lists with at least one admitted entry).  The warp
+// kernels above spend ~260 warp instructions per point on shuffles; a sequential ML-way merge
+// of the sorted lists needs ~25 steps of ~40 instructions per THREAD, so the stage becomes a
+// plain streaming pass over the lists.  A CTA stages the lists of its PT points in shared
+// memory with coalesced 16-byte loads (row of a point: [list][k] distances, [list][k] ids, the
+// output row, padded to 16 mod 32 words), each thread then walks its own row: the heads of the
+// lists live in registers (static indexing), the smallest head is emitted unless it repeats the
+// id emitted last (equal ids carry equal distances, so duplicates are adjacent in the merged
+// order), and an equal distance with a DIFFERENT id among the kept entries (or across the
+// keep/drop boundary) reports the row to the literal kernel, as in the warp kernels.
+struct MergeThreadArgs {
+  int n_src;                 // lists staged: those with admit > 0, then (if not among them) the corner list
+  int src[17];               // original list index
+  int admit[17];
+  int corner_slot, corner_pos;   // staged slot of the corner list, or -1
+};
+
+template <int ML>
+__global__ void __launch_bounds__(64)
+merge_lists_thread_kernel(const u32 *__restrict__ lists_ids, const FT *__restrict__ lists_dist,
+                          MergeThreadArgs a, size_t n, u32 sentinel, int k, int row_words,
+                          u32 *__restrict__ out_ids, FT *__restrict__ out_dist, TieList ties) {
+  constexpr int PT = 64;
+  constexpr int FW = sizeof(FT) / 4;                              // words per distance
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u32 *sm = reinterpret_cast<u32 *>(smem_raw);
+  const int tid = threadIdx.x;
+  const size_t x0 = (size_t)blockIdx.x * PT;
+  const int pts = (int)min((size_t)PT, n - x0);
+  const int NS = a.n_src;
+  // row layout (words): dist [NS][k] (FW words each) | out dist [k] | ids [NS][k] | out ids [k]
+  const int off_od = NS * k * FW, off_ids = off_od + k * FW, off_oi = off_ids + NS * k;
+  // ---- stage: for every list, the pts*k entries of this CTA are contiguous in global memory
+  for (int s = 0; s < NS; s++) {
+    const size_t g0 = ((size_t)a.src[s] * n + x0) * k;
+    const int cells = pts * k;
+    if ((k & 3) == 0 && FW == 1) {
+      const uint4 *gi = reinterpret_cast<const uint4 *>(lists_ids + g0);
+      const uint4 *gd = reinterpret_cast<const uint4 *>(lists_dist + g0);
+      for (int e = tid; e < cells / 4; e += PT) {
+        const int p = (4 * e) / k, z = 4 * e - p * k;
+        *reinterpret_cast<uint4 *>(sm + (size_t)p * row_words + off_ids + s * k + z) = gi[e];
+        *reinterpret_cast<uint4 *>(sm + (size_t)p * row_words + (s * k + z) * FW) = gd[e];
+      }
+    } else {
+      for (int e = tid; e < cells; e += PT) {
+        const int p = e / k, z = e - p * k;
+        sm[(size_t)p * row_words + off_ids + s * k + z] = lists_ids[g0 + e];
+        *reinterpret_cast<FT *>(sm + (size_t)p * row_words + (s * k + z) * FW) = lists_dist[g0 + e];
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < pts) {
+    u32 *row = sm + (size_t)tid * row_words;
+    const FT *rd = reinterpret_cast<const FT *>(row);
+    const u32 *ri = row + off_ids;
+    FT *od = reinterpret_cast<FT *>(row + off_od);
+    u32 *oi = row + off_oi;
+    const FT inf = ft_inf();
+    FT hv[ML];
+    u32 hid[ML];
+    int hp[ML];
+#pragma unroll
+    for (int s = 0; s < ML; s++) {
+      const bool on = s < NS && a.admit[s] > 0;
+      hv[s] = on ? rd[s * k] : inf;
+      hid[s] = on ? ri[s * k] : sentinel;
+      hp[s] = 0;
+    }
+    int out = 0;
+    u32 last_id = sentinel;
+    FT last_v = -inf;
+    bool tie = false;
+    for (;;) {
+      FT bv = hv[0];
+      int bl = 0;
+#pragma unroll
+      for (int s = 1; s < ML; s++)
+        if (hv[s] < bv) { bv = hv[s]; bl = s; }
+      if (bv == inf) break;
+      u32 bid = hid[0];
+      int bp = hp[0];
+#pragma unroll
+      for (int s = 1; s < ML; s++)
+        if (s == bl) { bid = hid[s]; bp = hp[s]; }
+      if (bid != last_id || out == 0) {
+        if (bv == last_v && out > 0) tie = true;                  // equal distance, different id, earlier one kept
+        if (out == k) break;                                      // the first dropped entry has been looked at
+        od[out] = bv;
+        oi[out] = bid;
+        out++;
+        last_id = bid;
+        last_v = bv;
+      }
+      // advance list bl
+      bp++;
+      FT nv = inf;
+      u32 ni = sentinel;
+      const int lim = a.admit[bl];
+      if (bp < lim) { nv = rd[bl * k + bp]; ni = ri[bl * k + bp]; }
+#pragma unroll
+      for (int s = 0; s < ML; s++)
+        if (s == bl) { hv[s] = nv; hid[s] = ni; hp[s] = bp; }
+    }
+    // prefix corner: the largest admitted entry dies if its id sits in the first slot
+    // outside the prefix and no admitted entry is infinite
+    if (a.corner_slot >= 0) {
+      bool any_inf = false;
+      FT max_v = -inf;
+      u32 max_id = sentinel;
+      for (int s = 0; s < NS; s++) {
+        int e = a.admit[s] - 1;
+        while (e >= 0 && rd[s * k + e] == inf) { any_inf = true; e--; }
+        if (e >= 0 && rd[s * k + e] > max_v) { max_v = rd[s * k + e]; max_id = ri[s * k + e]; }
+      }
+      if (!any_inf && out > 0) {
+        const u32 cid = ri[a.corner_slot * k + a.corner_pos];
+        if (cid == max_id && oi[out - 1] == cid) out--;           // the largest entry is the last one kept
+      }
+    }
+    for (int e = out; e < k; e++) { od[e] = inf; oi[e] = sentinel; }
+    if (tie && ties.rows) tie_report(ties, (u32)(x0 + tid));
+  }
+  __syncthreads();
+  // ---- coalesced copy-out of the pts output rows
+  for (int e = tid; e < pts * k; e += PT) {
+    const int p = e / k, z = e - p * k;
+    out_ids[(x0 + p) * (size_t)k + z] = sm[(size_t)p * row_words + off_oi + z];
+    out_dist[(x0 + p) * (size_t)k + z] = *reinterpret_cast<const FT *>(sm + (size_t)p * row_words + off_od + z * FW);
+  }
+}
+
 // Literal row: the n_lists lists of a point side by side (k*n_lists slots), the reference's
 // network, first k slots out.  One CTA per reported row (ties.rows == NULL: every row — rows
 // shorter than 16 slots).
@@ -225,6 +358,14 @@ merge_literal_kernel(const u32 *__restrict__ lists_ids, const FT *__restrict__ l
   }
 }
 
+// 1 (default): the thread-per-point merge where it applies; 0: the warp kernels (same rows)
+static int merge_thread_mode = -1;
+extern "C" void annb_merge_thread_mode(int on) { merge_thread_mode = on ? 1 : 0; }
+static int merge_thread_enabled() {
+  if (merge_thread_mode < 0) { const char *e = getenv("ANN_B200_THREAD_MERGE"); merge_thread_mode = (e && *e) ? (*e != '0') : 1; }
+  return merge_thread_mode;
+}
+
 extern "C" void annb_merge_lists(const u32 *lists_ids, const FT *lists_dist, int n_lists,
                                  const int *host_admit, int corner_list, int corner_pos,
                                  const u32 *merged_in_ids, const FT *merged_in_dist, size_t n,
@@ -251,7 +392,45 @@ extern "C" void annb_merge_lists(const u32 *lists_ids, const FT *lists_dist, int
   TieList f = whole_row ? ls.list : all_rows;        // rows == NULL: ties are not recorded
   dim3 block(256), grid(grid_for(n * 32, 256));
   const char *nofast = getenv("ANN_B200_NO_FAST_MERGE");
-  if (k <= 16 && merged_in_ids == NULL && !(nofast && *nofast && *nofast != '0')) {
+  bool threaded = false;
+  if (merged_in_ids == NULL && merge_thread_enabled()) {
+    MergeThreadArgs ta;
+    ta.n_src = 0;
+    ta.corner_slot = -1;
+    ta.corner_pos = corner_pos;
+    bool fits = true;
+    for (int i = 0; i < n_lists && fits; i++)
+      if (host_admit[i] > 0 || i == corner_list) {
+        if (ta.n_src == 17) { fits = false; break; }
+        if (i == corner_list) ta.corner_slot = ta.n_src;
+        ta.src[ta.n_src] = i;
+        ta.admit[ta.n_src] = host_admit[i];
+        ta.n_src++;
+      }
+    int live = 0;
+    for (int i = 0; i < ta.n_src; i++) live += ta.admit[i] > 0;
+    const int FW = (int)(sizeof(FT) / 4);
+    int row_words = (ta.n_src * (int)k + (int)k) * (1 + FW);
+    row_words += (16 - (row_words & 31) + 32) & 31;                // = 16 mod 32: two points never share a bank phase
+    if ((row_words & 3) != 0) row_words = (row_words + 3) & ~3;
+    const size_t tsmem = (size_t)row_words * 4 * 64;
+    if (fits && live >= 1 && live <= 16 && ta.n_src <= 17 && tsmem <= 200 * 1024) {
+      // the corner list (admit 0) is staged but never a merge source; sources must sit in slots < ML
+      const bool big = live > 8 || ta.n_src > 8;
+      static size_t configured[2] = {0, 0};
+      if (tsmem > configured[big]) {
+        if (big) RT_CHECK(cudaFuncSetAttribute(merge_lists_thread_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        else RT_CHECK(cudaFuncSetAttribute(merge_lists_thread_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured[big] = 200 * 1024;
+      }
+      unsigned tgrid = (unsigned)((n + 63) / 64);
+      if (big) merge_lists_thread_kernel<17><<<tgrid, 64, tsmem, stream>>>(lists_ids, lists_dist, ta, n, (u32)sentinel_n, (int)k, row_words, merged_ids, merged_dist, f);
+      else merge_lists_thread_kernel<8><<<tgrid, 64, tsmem, stream>>>(lists_ids, lists_dist, ta, n, (u32)sentinel_n, (int)k, row_words, merged_ids, merged_dist, f);
+      threaded = true;
+    }
+  }
+  if (threaded) {
+  } else if (k <= 16 && merged_in_ids == NULL && !(nofast && *nofast && *nofast != '0')) {
     merge_lists_fast_kernel<<<grid, block, 0, stream>>>(lists_ids, lists_dist, a, n, (u32)sentinel_n, (int)k, merged_ids, merged_dist, f);
   } else
   switch (regs) {
@@ -620,11 +799,28 @@ static void launch_supercharge(int regs, size_t smem, annb_stream stream, const 
   LAUNCH_CHECK("supercharge_literal");
 }
 
+#ifdef USE_FLOAT
+#include "annb_supercharge_screen.cuh"
+static int s5_screen_mode = -1;
+extern "C" void annb_supercharge_screen_mode(int on) { s5_screen_mode = on ? 1 : 0; }
+static int s5_screen_enabled() {
+  if (s5_screen_mode < 0) { const char *e = getenv("ANN_B200_S5_SCREEN"); s5_screen_mode = (e && *e) ? (*e != '0') : 1; }
+  return s5_screen_mode;
+}
+extern "C" int annb_supercharge_screen_applies(size_t d, size_t k) {
+  return s5_screen_enabled() && (d == 16 || d == 32 || d == 64 || d == 128) && k <= 32 && k * (k + 1) >= 16;
+}
+#else
+extern "C" int annb_supercharge_screen_applies(size_t d, size_t k) { (void)d; (void)k; return 0; }
+extern "C" void annb_supercharge_screen_mode(int on) { (void)on; }
+extern "C" void annb_supercharge_screen_stats(unsigned long long out[2], int reset) { (void)reset; out[0] = out[1] = 0; }
+#endif
+
 extern "C" void annb_supercharge(const FT *queries, const FT *points, const u32 *own_ids,
                                  const FT *own_dist, const u32 *graph, size_t n, size_t d, size_t k,
                                  size_t row_begin, size_t row_end, int exclude_self,
                                  u32 *out_ids, FT *out_dist, void *scratch, size_t scratch_bytes,
-                                 int *status, annb_stream stream) {
+                                 int *status, const annb_supercharge_opts *opts, annb_stream stream) {
   if (row_end <= row_begin) return;
   int regs = list_regs(k);
   if (!regs) fatal_config("k > 256");
@@ -636,11 +832,32 @@ extern "C" void annb_supercharge(const FT *queries, const FT *points, const u32 
   const bool all_literal = k * (k + 1) < 16;      // the network degenerates: literal rows only
   bool all_literal_redo_only = false;             // fast kernel already ran: only the reported redo
   RT_CHECK(cudaMemsetAsync(ls.list.count, 0, sizeof(u32), stream));
+  const u32 *row_perm = opts ? opts->row_perm : NULL;
+#ifdef USE_FLOAT
+  // screened path: precomp only (the queries are the points, so their fp16 rows exist)
+  if (opts && opts->points16 && opts->scale_bits && exclude_self && queries == points &&
+      annb_supercharge_screen_applies(d, k)) {
+    const size_t ssmem = k * k * sizeof(u32) * 8;
+    dim3 block(256), grid(grid_for(rows * 32, 256));
+    const unsigned short *p16 = (const unsigned short *)opts->points16;
+#define SCREEN_CASE(DD) supercharge_screen_kernel<DD><<<grid, block, ssmem, stream>>>(points, p16, opts->scale_bits, own_ids, own_dist, graph, n, (int)k, row_begin, row_end, row_perm, out_ids, out_dist, ls.list)
+    switch (d) {
+      case 16: SCREEN_CASE(16); break;
+      case 32: SCREEN_CASE(32); break;
+      case 64: SCREEN_CASE(64); break;
+      default: SCREEN_CASE(128); break;
+    }
+#undef SCREEN_CASE
+    LAUNCH_CHECK("supercharge_screen");
+    all_literal_redo_only = true;
+  } else
+#endif
   // fast path
   {
     const char *off = getenv("ANN_B200_NO_FAST_SUPERCHARGE");
     bool allow = !(off && *off && *off != '0');
     int epl = (d == 16 || d == 32 || d == 64 || d == 128) ? (int)(d / 8) : 0;
+    if (row_perm) fatal_config("row_perm without the screened supercharge");
     if (allow && !all_literal && k <= 32 && epl) {
       size_t fsmem = k * k * sizeof(u32) * 8;
       dim3 block(256), grid(grid_for(rows * 32, 256));

@@ -12,7 +12,7 @@
 //   leaf_literal_kernel     redoes the (rare) rows in which an exact distance tie could
 //                           matter with the reference's literal row + sorting network.
 #include "annb_common.cuh"
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 static __device__ unsigned long long leaf_literal_rows_dev;
 static __device__ unsigned long long leaf_pairs_dev;      // (point, real candidate) pairs measured by S3
@@ -681,6 +681,9 @@ extern "C" void annb_gather_rows_screen(const FT *, const u32 *, size_t, size_t,
                                         void *, annb_stream) {
   fatal_config("screened leaf path in the double build");
 }
+extern "C" void annb_screen_prep_points(const FT *, const FT *, size_t, size_t, const unsigned *, void *, annb_stream) {
+  fatal_config("fp16 screen in the double build");
+}
 #endif
 // fp16 copy, norms, scale word and the overflow bucket list of the screened path
 static size_t screen_area_bytes(size_t n, size_t d, size_t d_short, size_t k) {
@@ -746,6 +749,15 @@ extern "C" void annb_gather_rows_screen(const FT *points, const u32 *order, size
   screen_prep_kernel<<<grid_for(n * (d / 4), 256), 256, 0, stream>>>(points, order, sorted_points, mean, n, (int)d,
                                                                     scale_bits, a.sp16, a.nrm);
   LAUNCH_CHECK("gather_rows_screen");
+}
+
+// fp16 copy of the points in original order (the screened supercharge reads it)
+extern "C" void annb_screen_prep_points(const FT *points, const FT *mean, size_t n, size_t d,
+                                        const unsigned *scale_bits, void *points16, annb_stream stream) {
+  if (d % 4 || d / 4 > 32 || ((d / 4) & (d / 4 - 1))) fatal_config("annb_screen_prep_points: d must be 4..128, a power of two");
+  screen_prep_kernel<<<grid_for(n * (d / 4), 256), 256, 0, stream>>>(points, NULL, NULL, mean, n, (int)d, scale_bits,
+                                                                    (unsigned short *)points16, NULL);
+  LAUNCH_CHECK("screen_prep_points");
 }
 
 template <int D>

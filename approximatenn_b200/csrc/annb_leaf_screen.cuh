@@ -49,7 +49,6 @@ extern "C" unsigned long long annb_leaf_overflow_buckets(int reset) {
   return v;
 }
 
-static constexpr float SCREEN_SQRT_KAPPA = 0.03226f;   // kappa = 0.00104
 
 // max |x - mean| over the set, as the bits of a non-negative float
 __global__ void __launch_bounds__(256)
@@ -111,7 +110,7 @@ screen_prep_kernel(const float *__restrict__ src, const u32 *__restrict__ order,
     packed.x = *reinterpret_cast<unsigned *>(&p01);
     packed.y = *reinterpret_cast<unsigned *>(&p23);
     reinterpret_cast<uint2 *>(sp16 + row * (size_t)d)[l] = packed;
-    if (l == 0) {
+    if (l == 0 && nrm) {
       float s = sqrtf(ss) * (1.0f + 1.0f / 4096.0f) + sqrtf((float)d) * (1.0f / 16384.0f);
       nrm[row] = make_float2(s * SCREEN_SQRT_KAPPA, n2);
     }

@@ -145,11 +145,35 @@ void annb_merge_lists(const annb_u32 *lists_ids, const ftype *lists_dist, int n_
  * id == x only when the query set IS the point set (compute.cl:145).
  * graph may be the merged ids themselves (precomp) or save->graph (query).
  * scratch: at least (row_end-row_begin) + 512 bytes plus room for literal rows.           */
+/* opts (may be NULL): extras of the precomp path, where the queries ARE the points.
+ *   points16/scale_bits  fp16 copy of the points in original order (annb_screen_prep_points) and
+ *                        its scale word: candidates are bracketed from it and only those that can
+ *                        reach the row's k best are measured exactly (float, d in {16,32,64,128},
+ *                        k <= 32; same rows bit for bit; ANN_B200_S5_SCREEN=0 switches it off)
+ *   row_perm             a permutation of [row_begin, row_end) (indexed by row): the order in
+ *                        which the rows are worked on (locality), NULL = ascending                */
+typedef struct {
+  const void *points16;
+  const unsigned *scale_bits;
+  const annb_u32 *row_perm;
+} annb_supercharge_opts;
 void annb_supercharge(const ftype *queries, const ftype *points, const annb_u32 *own_ids,
                       const ftype *own_dist, const annb_u32 *graph, size_t n, size_t d,
                       size_t k, size_t row_begin, size_t row_end, int exclude_self,
                       annb_u32 *out_ids, ftype *out_dist, void *scratch, size_t scratch_bytes,
-                      int *status, annb_stream stream);
+                      int *status, const annb_supercharge_opts *opts, annb_stream stream);
+/* 1 (default) / 0: the screened supercharge and the thread-per-point merge can be switched off at
+ * run time (ANN_B200_S5_SCREEN=0, ANN_B200_THREAD_MERGE=0 do the same); results are identical  */
+void annb_supercharge_screen_mode(int on);
+void annb_merge_thread_mode(int on);
+/* 1 if annb_supercharge will use points16 for this shape                                       */
+int annb_supercharge_screen_applies(size_t d, size_t k);
+/* fp16 copy of the points in ORIGINAL order for the screened supercharge: c' = fp16((x - mean)
+ * * scale), scale from the word annb_screen_scale() wrote.  points16: n*d*2 bytes.              */
+void annb_screen_prep_points(const ftype *points, const ftype *mean, size_t n, size_t d,
+                             const unsigned *scale_bits, void *points16, annb_stream stream);
+/* candidates the screened supercharge bracketed [0] and measured exactly [1] since the last reset */
+void annb_supercharge_screen_stats(unsigned long long out[2], int reset);
 
 /* ---- query path (alg.c:438-519) ----------------------------------------------------------
  * annb_query_hash: prods + add_up_cols + compute_signs (compute.cl:268-275,160-167,223-231):
