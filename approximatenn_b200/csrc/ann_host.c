@@ -54,8 +54,8 @@ static struct {
   /* one device arena reused across calls; grown on demand, released by gpu_cleanup()  */
   char *arena;
   size_t arena_bytes, arena_used;
-  size_t *table_buf;           /* staging for exported bucket tables, grown geometrically  */
-  size_t table_cap;
+  annb_u32 *table_buf;         /* exported 32-bit bucket tables when no query cache takes them */
+  size_t table_cap;            /* cells */
   annh_stage_times last;
   int timing;
   cudaEvent_t ev[2 * ANNH_MAX_SPANS];
@@ -334,6 +334,34 @@ static void validate(size_t n, size_t k, size_t d, int tries, size_t len_b, size
   if (2 * len_a > d_short) annh_fatal("%s", "2*rot_len_after must not exceed d_short (alg.c:66)");
 }
 
+/* save->which_par / par_maxes once every try's largest bucket is known (alg.c:270-271,376-377):
+ * host arrays malloc()ed here, device tables (32-bit cells) in the query cache's own buffers
+ * when it adopts this index, else in one library-owned block; dtab[t] receives the addresses.  */
+static annh_tables *save_tables_begin(save_t *save, const annb_u32 *h_tm, size_t T, size_t buckets,
+                                      int adopt, annb_u32 **dtab) {
+  size_t *cells = malloc(sizeof(size_t) * T), total = 0;
+  for (size_t t = 0; t < T; t++) {
+    cells[t] = buckets * (size_t)h_tm[t];
+    total += (cells[t] + 63) & ~(size_t)63;
+    save->par_maxes[t] = h_tm[t];
+    save->which_par[t] = malloc((cells[t] ? cells[t] : 1) * sizeof(size_t));
+    if (!save->which_par[t]) annh_fatal("%s", "out of host memory for the bucket tables");
+  }
+  if (!adopt && total > G.table_cap) {
+    if (G.table_buf) CK(cudaFree(G.table_buf));
+    G.table_cap = total + total / 4 + 1024;
+    CK(cudaMalloc((void **)&G.table_buf, G.table_cap * sizeof(annb_u32)));
+  }
+  size_t at = 0;
+  for (size_t t = 0; t < T; t++) {
+    dtab[t] = adopt ? annh_index_table_buffer((int)t, cells[t]) : G.table_buf + at;
+    at += (cells[t] + 63) & ~(size_t)63;
+  }
+  annh_tables *tb = annh_tables_begin((int)T, cells, save->which_par, G.device);
+  free(cells);
+  return tb;
+}
+
 size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries,
                     size_t rots_before, size_t rot_len_before, size_t rots_after,
                     size_t rot_len_after, save_t *save, ftype **dists_o) {
@@ -409,7 +437,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
                  pad256(annb_hash_scratch_bytes(&desc)) +
                  pad256(scratch_bytes) + 8192 + 256;
   const int s5_screened = annb_supercharge_screen_applies(d, k);
-  if (s5_screened) fixed += pad256(n * d * 2);                /* fp16 copy of the points, original order */
+  if (s5_screened) fixed += pad256(n * d * 2) + pad256(n * 8); /* fp16 copy of the points (original order) + norms */
   if (sharded && save) fixed += pad256(T * n * 4);            /* every try's hashes, for the tables */
   if (sharded)   /* merged ids (all rows), merged dists + results (own rows), exchanged lists */
     fixed += pad256(np * k * 4) + pad256(my_rows * k * w) + pad256(my_rows * k * 4) + pad256(my_rows * k * w) +
@@ -456,6 +484,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   unsigned *dscreen = annh_arena_take(256);                     /* scale word of the screened S3 path */
   const int screened = annb_screen_applies(d, d_short, k);
   void *dX16 = s5_screened ? annh_arena_take(n * d * 2) : NULL;
+  void *dN16 = s5_screened ? annh_arena_take(n * 8) : NULL;
   annb_u32 *dhash_all = (sharded && save) ? annh_arena_take(T * n * 4) : NULL;
   annb_u32 *ds_ids = sharded ? annh_arena_take(T * my_rows * k * 4) : NULL;   /* [T][my_rows][k] */
   ftype *ds_dist = sharded ? annh_arena_take(T * my_rows * k * w) : NULL;
@@ -474,6 +503,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   if (Tl) CK(cudaMemcpyAsync(d_permb, h_permb, Tl * d_max * 4, cudaMemcpyHostToDevice, st));
   if (d_short && Tl) CK(cudaMemcpyAsync(d_pick, h_pick, Tl * d_short * 4, cudaMemcpyHostToDevice, st));
   desc.plane_idx = d_idx; desc.plane_cs = d_cs; desc.perm_b = d_permb; desc.pick = d_pick;
+  desc.host_plane_idx = h_idx; desc.host_plane_cs = h_cs; desc.host_perm_b = h_permb; desc.host_pick = h_pick;
 
   HP("upload enqueued");
   /* 4. S0 column means (alg.c:367-368); the accumulator borrows the sorted-copy buffer */
@@ -493,7 +523,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   }
   annb_scale_means(dXs, n, d, dmean, st);
   if ((screened && Tl) || s5_screened) annb_screen_scale(dX, dmean, n, d, dscreen, st);
-  if (s5_screened) annb_screen_prep_points(dX, dmean, n, d, dscreen, dX16, st);
+  if (s5_screened) annb_screen_prep_points(dX, dmean, n, d, dscreen, dX16, dN16, st);
 
   /* 5. S1 hashes of every owned try in one pass over the points                         */
   span_end(sp);
@@ -502,6 +532,8 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   span_end(sp);
 
   int adopt = 0;
+  annh_tables *tb = NULL;
+  annb_u32 **dtab = NULL, *h_tm_all = NULL;
   if (save && !sharded) adopt = annh_index_adopt_begin(n, k, d_short, d, T);
   if (save) {
     save->tries = tries; save->n = n; save->k = k; save->d_short = d_short; save->d_long = d;
@@ -509,10 +541,22 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
     save->which_par = malloc(sizeof(size_t *) * T);
     save->par_maxes = malloc(sizeof(size_t) * T);
     save->bases = malloc(w * T * d_short * d);
+    dtab = malloc(sizeof(annb_u32 *) * T);
+    h_tm_all = malloc(sizeof(annb_u32) * T);
     CK(cudaMemcpyAsync(save->row_means, dmean, d * w, cudaMemcpyDeviceToHost, st));
-    for (size_t t = 0; t < T; t++)
+    if (!sharded) {
+      /* every try's largest bucket first (a histogram each), ONE synchronisation, and from then on
+       * the tables leave as 32-bit cells behind the tries without stopping the stream             */
+      for (size_t t = 0; t < T; t++) annb_bucket_max(dhash + t * n, n, buckets, dcount, dtmax + t, st);
+      CK(cudaMemcpyAsync(h_tm_all, dtmax, 4 * T, cudaMemcpyDeviceToHost, st));
+    }
+    for (size_t t = 0; t < T; t++)                 /* host work while the device hashes */
       projection_rows(tf + t, rots_before, rot_len_before, rots_after, rot_len_after, d_short, d,
                       d_max, save->bases + t * d_short * d);
+    if (!sharded) {
+      CK(cudaStreamSynchronize(st));
+      tb = save_tables_begin(save, h_tm_all, T, buckets, adopt, dtab);
+    }
   }
 
   /* 6. per owned try: S2 bucket tables, S3 k best; merge whenever `group` lists wait      */
@@ -534,23 +578,9 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
       const annb_u32 *hash_t = dhash + (j0 + j) * n;
       sp = span_begin(3);
       annb_build_buckets(hash_t, n, buckets, dcount, doffset, dorder_tmp, dorder, dtmax + t, dscan, st);
-      if (save && !sharded) {                      /* padded table for save->which_par[t] */
-        annb_u32 tm = 0;
-        CK(cudaMemcpyAsync(&tm, dtmax + t, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        size_t cells = buckets * (size_t)tm;
-        if (cells > G.table_cap) {
-          if (G.table_buf) CK(cudaFree(G.table_buf));
-          G.table_cap = cells + cells / 2 + 1024;
-          CK(cudaMalloc((void **)&G.table_buf, G.table_cap * sizeof(size_t)));
-        }
-        size_t *dtable = G.table_buf;
-        annb_export_table(doffset, dorder, n, buckets, tm, dtable, st);
-        if (adopt) annh_index_adopt_table((int)t, dtable, cells);
-        save->par_maxes[t] = tm;
-        save->which_par[t] = malloc((cells ? cells : 1) * sizeof(size_t));
-        annh_prefault(save->which_par[t], cells * sizeof(size_t));
-        CK(cudaMemcpyAsync(save->which_par[t], dtable, cells * sizeof(size_t), cudaMemcpyDeviceToHost, st));
+      if (tb) {                                    /* padded table for save->which_par[t] */
+        annb_export_table32(doffset, dorder, n, buckets, h_tm_all[t], dtab[t], st);
+        annh_tables_submit(tb, (int)t, dtab[t], st);
       }
       if (screened) annb_gather_rows_screen(dX, dorder, n, d, dmean, dscreen, dXs, dscratch, st);
       else annb_gather_rows(dX, dorder, n, d, dXs, st);
@@ -597,7 +627,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   /* 7. S5 supercharging of the owned rows (alg.c:313-327); graph = the merged lists        */
   {
     annb_supercharge_opts s5;
-    s5.points16 = dX16; s5.scale_bits = dscreen; s5.row_perm = NULL;
+    s5.points16 = dX16; s5.nrm = dN16; s5.scale_bits = dscreen; s5.row_perm = NULL;
     int nch = full_result && sharded ? 1 : annh_egress_chunks(eg);
     for (int c = 0; c < nch; c++) {
       size_t r0 = row_lo + ((my_rows * (size_t)c / nch) & ~(size_t)31);
@@ -624,22 +654,14 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
       CK(cudaMemcpyAsync(dhash_all + own[j] * n, dhash + j * n, n * 4, cudaMemcpyDeviceToDevice, st));
     for (size_t t = 0; t < T; t++)
       annh_dist_broadcast(dhash_all + t * n, n * 4, annb200_dist_try_owner((int)t, R), st);
+    for (size_t t = 0; t < T; t++) annb_bucket_max(dhash_all + t * n, n, buckets, dcount, dtmax + t, st);
+    CK(cudaMemcpyAsync(h_tm_all, dtmax, 4 * T, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    tb = save_tables_begin(save, h_tm_all, T, buckets, 0, dtab);
     for (size_t t = 0; t < T; t++) {
       annb_build_buckets(dhash_all + t * n, n, buckets, dcount, doffset, dorder_tmp, dorder, dtmax + t, dscan, st);
-      annb_u32 tm = 0;
-      CK(cudaMemcpyAsync(&tm, dtmax + t, 4, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      size_t cells = buckets * (size_t)tm;
-      if (cells > G.table_cap) {
-        if (G.table_buf) CK(cudaFree(G.table_buf));
-        G.table_cap = cells + cells / 2 + 1024;
-        CK(cudaMalloc((void **)&G.table_buf, G.table_cap * sizeof(size_t)));
-      }
-      annb_export_table(doffset, dorder, n, buckets, tm, G.table_buf, st);
-      save->par_maxes[t] = tm;
-      save->which_par[t] = malloc((cells ? cells : 1) * sizeof(size_t));
-      annh_prefault(save->which_par[t], cells * sizeof(size_t));
-      CK(cudaMemcpyAsync(save->which_par[t], G.table_buf, cells * sizeof(size_t), cudaMemcpyDeviceToHost, st));
+      annb_export_table32(doffset, dorder, n, buckets, h_tm_all[t], dtab[t], st);
+      annh_tables_submit(tb, (int)t, dtab[t], st);
     }
   }
   HP("supercharge enqueued");
@@ -660,6 +682,8 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
       annh_fatal("%s", "candidate rows shorter than 16 slots (n far too small for this k)");
   free(h_tmax);
 
+  if (tb) annh_tables_end(tb);
+  free(dtab); free(h_tm_all);
   if (save) save->graph = graph_copy;                           /* alg.c:428-432: two separate copies */
   if (adopt) annh_index_adopt_finish(save, points, dX, dmean, dout_ids);
   for (size_t t = 0; t < T; t++) free_transform(tf + t);

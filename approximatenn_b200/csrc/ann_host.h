@@ -46,6 +46,12 @@ size_t *annh_egress_end(annh_egress *e, ftype **dists_o, size_t **second_ids_o);
 void annh_prefault(void *ptr, size_t bytes);   /* touch the pages of a fresh allocation, 4 threads */
 void annh_egress_release(void);
 
+/* bucket tables of save_t leave as 32-bit cells and are widened by host threads (ann_results.c) */
+typedef struct annh_tables annh_tables;
+annh_tables *annh_tables_begin(int tries, const size_t *cells, size_t **host_tables, int device);
+void annh_tables_submit(annh_tables *tb, int t, const void *dev_table32, void *producer_stream);
+void annh_tables_end(annh_tables *tb);
+
 /* sharded execution (ann_dist.c); world == 1 unless annb200_dist_init() was called          */
 int annh_dist_rank(void);
 int annh_dist_world(void);
@@ -63,7 +69,7 @@ void annh_ingest_release(void);
 
 /* precomp_gpu(save != NULL) hands its device-resident data to the query cache (ann_query.c) */
 int annh_index_adopt_begin(size_t n, size_t k, size_t d_short, size_t d, size_t tries);
-void annh_index_adopt_table(int t, const size_t *dev_table, size_t cells);
+annb_u32 *annh_index_table_buffer(int t, size_t cells);   /* device buffer of try t's 32-bit table */
 void annh_index_adopt_finish(const save_t *s, const ftype *host_points, const ftype *dev_points,
                              const ftype *dev_mean, const annb_u32 *dev_graph);
 

@@ -185,11 +185,10 @@ int annh_index_adopt_begin(size_t n, size_t k, size_t d_short, size_t d, size_t 
   return 1;
 }
 
-/* dev_table: the size_t table of try t as exported for save->which_par[t] (still on the device) */
-void annh_index_adopt_table(int t, const size_t *dev_table, size_t cells) {
-  cudaStream_t st = (cudaStream_t)annh_stream();
+/* the cache's own buffer for try t's 32-bit table: precomp_gpu exports straight into it */
+annb_u32 *annh_index_table_buffer(int t, size_t cells) {
   reserve((void **)&IDX.d_tab[t], &IDX.cap_tab[t], cells * 4);
-  annb_narrow_ids(dev_table, cells, IDX.d_tab[t], st);
+  return IDX.d_tab[t];
 }
 
 void annh_index_adopt_finish(const save_t *s, const ftype *host_points, const ftype *dev_points,

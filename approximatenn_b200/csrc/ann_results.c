@@ -63,7 +63,9 @@ static struct {
   int ready;
 } S;
 
+static void tables_release(void);
 void annh_egress_release(void) {
+  tables_release();
   if (S.stage) CK(cudaFreeHost(S.stage));
   S.stage = NULL;
   S.stage_bytes = 0;
@@ -233,4 +235,119 @@ void annh_prefault(void *ptr, size_t bytes) {
     started++;
   }
   for (int i = 0; i < started; i++) pthread_join(th[i], NULL);
+}
+
+/* ---- bucket tables of save_t (which_par[t], alg.c:270-271) ------------------------------------
+ * The device exports a table with 32-bit cells; a copy stream moves it into pinned staging as
+ * soon as it exists and a few host threads widen it into the malloc()ed size_t array the API
+ * hands out, while the GPU works on the following tries.  Nothing here blocks the caller
+ * before annh_tables_end().                                                                  */
+#define TABLE_THREADS 3
+struct annh_tables {
+  int tries, device, nthreads;
+  size_t *cells;               /* [tries] */
+  size_t *at;                  /* [tries] offset (cells) into the staging buffer */
+  size_t **host;               /* [tries] destination arrays (owned by the caller's save_t) */
+  cudaEvent_t *done;           /* [tries] */
+  pthread_t th[TABLE_THREADS];
+  struct { struct annh_tables *tb; int idx; } arg[TABLE_THREADS];
+  pthread_mutex_t mu;
+  pthread_cond_t cv;
+  int submitted, closed;
+};
+static struct { annb_u32 *stage; size_t bytes; } TS;
+
+static void *tables_worker(void *p) {
+  struct annh_tables *tb = *(struct annh_tables **)p;        /* first member of the argument record */
+  const int me = (int)((char *)p - (char *)tb->arg) / (int)sizeof tb->arg[0];
+  cudaSetDevice(tb->device);
+  for (int t = 0;; t++) {
+    pthread_mutex_lock(&tb->mu);
+    while (t >= tb->submitted && !tb->closed) pthread_cond_wait(&tb->cv, &tb->mu);
+    int have = t < tb->submitted;
+    pthread_mutex_unlock(&tb->mu);
+    if (!have) break;
+    if (cudaEventSynchronize(tb->done[t]) != cudaSuccess) {
+      fprintf(stderr, "approximatenn_b200: table copy failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+      exit(1);
+    }
+    size_t lo = tb->cells[t] * (size_t)me / tb->nthreads, hi = tb->cells[t] * (size_t)(me + 1) / tb->nthreads;
+    const annb_u32 *src = TS.stage + tb->at[t];
+    size_t *dst = tb->host[t];
+    for (size_t i = lo; i < hi; i++) dst[i] = src[i];
+  }
+  return NULL;
+}
+
+annh_tables *annh_tables_begin(int tries, const size_t *cells, size_t **host_tables, int device) {
+  annh_tables *tb = calloc(1, sizeof *tb);
+  tb->tries = tries; tb->device = device;
+  tb->cells = malloc(sizeof(size_t) * tries);
+  tb->at = malloc(sizeof(size_t) * tries);
+  tb->host = malloc(sizeof(size_t *) * tries);
+  tb->done = malloc(sizeof(cudaEvent_t) * tries);
+  size_t total = 0;
+  for (int t = 0; t < tries; t++) {
+    tb->cells[t] = cells[t];
+    tb->at[t] = total;
+    total += (cells[t] + 63) & ~(size_t)63;
+    tb->host[t] = host_tables[t];
+    CK(cudaEventCreateWithFlags(&tb->done[t], cudaEventDisableTiming | cudaEventBlockingSync));
+  }
+  if (total * 4 + 256 > TS.bytes) {
+    if (TS.stage) CK(cudaFreeHost(TS.stage));
+    CK(cudaMallocHost((void **)&TS.stage, total * 4 + 256));
+    TS.bytes = total * 4 + 256;
+  }
+  if (!S.ready) {
+    CK(cudaStreamCreateWithFlags(&S.copy, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&S.produced, cudaEventDisableTiming));
+    S.ready = 1;
+  }
+  pthread_mutex_init(&tb->mu, NULL);
+  pthread_cond_init(&tb->cv, NULL);
+  long cores = sysconf(_SC_NPROCESSORS_ONLN);
+  tb->nthreads = cores >= 8 ? TABLE_THREADS : 1;
+  for (int i = 0; i < tb->nthreads; i++) {
+    tb->arg[i].tb = tb;
+    tb->arg[i].idx = i;
+    if (pthread_create(&tb->th[i], NULL, tables_worker, &tb->arg[i]) != 0) annh_fatal("%s", "pthread_create failed");
+  }
+  return tb;
+}
+
+/* tables must be submitted in try order 0, 1, ... */
+void annh_tables_submit(annh_tables *tb, int t, const void *dev_table32, void *producer_stream) {
+  if (t != tb->submitted) annh_fatal("%s", "internal: bucket tables submitted out of order");
+  cudaEvent_t produced;
+  CK(cudaEventCreateWithFlags(&produced, cudaEventDisableTiming));
+  CK(cudaEventRecord(produced, (cudaStream_t)producer_stream));
+  CK(cudaStreamWaitEvent(S.copy, produced, 0));
+  CK(cudaEventDestroy(produced));                  /* released once the wait has consumed it */
+  if (tb->cells[t])
+    CK(cudaMemcpyAsync(TS.stage + tb->at[t], dev_table32, tb->cells[t] * 4, cudaMemcpyDeviceToHost, S.copy));
+  CK(cudaEventRecord(tb->done[t], S.copy));
+  pthread_mutex_lock(&tb->mu);
+  tb->submitted++;
+  pthread_cond_broadcast(&tb->cv);
+  pthread_mutex_unlock(&tb->mu);
+}
+
+void annh_tables_end(annh_tables *tb) {
+  pthread_mutex_lock(&tb->mu);
+  tb->closed = 1;
+  pthread_cond_broadcast(&tb->cv);
+  pthread_mutex_unlock(&tb->mu);
+  for (int i = 0; i < tb->nthreads; i++) pthread_join(tb->th[i], NULL);
+  for (int t = 0; t < tb->tries; t++) CK(cudaEventDestroy(tb->done[t]));
+  pthread_mutex_destroy(&tb->mu);
+  pthread_cond_destroy(&tb->cv);
+  free(tb->cells); free(tb->at); free(tb->host); free(tb->done);
+  free(tb);
+}
+
+static void tables_release(void) {
+  if (TS.stage) CK(cudaFreeHost(TS.stage));
+  TS.stage = NULL;
+  TS.bytes = 0;
 }

@@ -16,10 +16,23 @@ extern unsigned long annb_g_launches;
 unsigned long long annb_leaf_literal_count(int reset);
 void annb_finish_literal_counts(unsigned long long out[2], int reset);
 
+// ANN_B200_DEBUG_SYNC=1: wait for every kernel right after its launch and name it on stderr
+// (finds the kernel that faults or never returns; never set in timed runs)
+static inline int annb_debug_sync() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("ANN_B200_DEBUG_SYNC"); v = e && *e && *e != '0'; }
+  return v;
+}
+
 #define LAUNCH_CHECK(what)                                                              \
   do {                                                                                  \
     annb_g_launches++;                                                                  \
     cudaError_t e_ = cudaGetLastError();                                                \
+    if (e_ == cudaSuccess && annb_debug_sync()) {                                       \
+      fprintf(stderr, "[debug-sync] %s launched\n", what);                              \
+      e_ = cudaDeviceSynchronize();                                                     \
+      fprintf(stderr, "[debug-sync] %s finished: %s\n", what, cudaGetErrorString(e_));  \
+    }                                                                                   \
     if (e_ != cudaSuccess) {                                                            \
       fprintf(stderr, "approximatenn_b200: launch of %s failed: %s\n", what,            \
               cudaGetErrorString(e_));                                                  \

@@ -491,7 +491,7 @@ supercharge_kernel(const FT *__restrict__ queries, const FT *__restrict__ points
   for (int o = 16; o >= 1; o >>= 1) {
     FT ov = __shfl_xor_sync(FULL, max_v, o);
     u32 oi = __shfl_xor_sync(FULL, max_id, o);
-    if (ov > max_v) { max_v = ov; max_id = oi; }
+    if (ov > max_v || (ov == max_v && oi < max_id)) { max_v = ov; max_id = oi; }   // uniform on ties
   }
   FT tau = best.kth(k);
   // equal neighbours inside the own list: the network decides their final order
@@ -608,7 +608,7 @@ supercharge_fast_kernel(const FT *__restrict__ queries, const FT *__restrict__ p
   for (int o = 16; o >= 1; o >>= 1) {
     FT ov = __shfl_xor_sync(FULL, max_v, o);
     u32 oi = __shfl_xor_sync(FULL, max_id, o);
-    if (ov > max_v) { max_v = ov; max_id = oi; }
+    if (ov > max_v || (ov == max_v && oi < max_id)) { max_v = ov; max_id = oi; }   // uniform on ties
   }
   FT tau = best.kth(k);
   // candidate ids -> uniq[0..U): pads and (in precomp) the point itself are dropped here
@@ -690,7 +690,7 @@ supercharge_fast_kernel(const FT *__restrict__ queries, const FT *__restrict__ p
   for (int o = 16; o >= 1; o >>= 1) {
     FT ov = __shfl_xor_sync(FULL, lmax_v, o);
     u32 oi = __shfl_xor_sync(FULL, lmax_id, o);
-    if (ov > lmax_v) { lmax_v = ov; lmax_id = oi; }
+    if (ov > lmax_v || (ov == lmax_v && oi < lmax_id)) { lmax_v = ov; lmax_id = oi; }   // uniform on ties
   }
   if (lmax_v > max_v) { max_v = lmax_v; max_id = lmax_id; }
   if (P2 < wide && !any_inf) {
@@ -800,6 +800,7 @@ static void launch_supercharge(int regs, size_t smem, annb_stream stream, const 
 }
 
 #ifdef USE_FLOAT
+#include "annb_screen_common.cuh"
 #include "annb_supercharge_screen.cuh"
 static int s5_screen_mode = -1;
 extern "C" void annb_supercharge_screen_mode(int on) { s5_screen_mode = on ? 1 : 0; }
@@ -835,12 +836,13 @@ extern "C" void annb_supercharge(const FT *queries, const FT *points, const u32 
   const u32 *row_perm = opts ? opts->row_perm : NULL;
 #ifdef USE_FLOAT
   // screened path: precomp only (the queries are the points, so their fp16 rows exist)
-  if (opts && opts->points16 && opts->scale_bits && exclude_self && queries == points &&
+  if (opts && opts->points16 && opts->nrm && opts->scale_bits && exclude_self && queries == points &&
       annb_supercharge_screen_applies(d, k)) {
-    const size_t ssmem = k * k * sizeof(u32) * 8;
+    const size_t ssmem = ((k * k + 9) & ~(size_t)1) * sizeof(u32) * 8;
     dim3 block(256), grid(grid_for(rows * 32, 256));
     const unsigned short *p16 = (const unsigned short *)opts->points16;
-#define SCREEN_CASE(DD) supercharge_screen_kernel<DD><<<grid, block, ssmem, stream>>>(points, p16, opts->scale_bits, own_ids, own_dist, graph, n, (int)k, row_begin, row_end, row_perm, out_ids, out_dist, ls.list)
+    const float2 *pn = (const float2 *)opts->nrm;
+#define SCREEN_CASE(DD) supercharge_screen_kernel<DD><<<grid, block, ssmem, stream>>>(points, p16, pn, opts->scale_bits, own_ids, own_dist, graph, n, (int)k, row_begin, row_end, row_perm, out_ids, out_dist, ls.list)
     switch (d) {
       case 16: SCREEN_CASE(16); break;
       case 32: SCREEN_CASE(32); break;

@@ -492,6 +492,7 @@ leaf_topk_tile_kernel(const FT *__restrict__ sp, const u32 *__restrict__ order,
 }
 
 #ifdef USE_FLOAT
+#include "annb_screen_common.cuh"
 #include "annb_leaf_screen.cuh"
 #endif
 
@@ -681,7 +682,7 @@ extern "C" void annb_gather_rows_screen(const FT *, const u32 *, size_t, size_t,
                                         void *, annb_stream) {
   fatal_config("screened leaf path in the double build");
 }
-extern "C" void annb_screen_prep_points(const FT *, const FT *, size_t, size_t, const unsigned *, void *, annb_stream) {
+extern "C" void annb_screen_prep_points(const FT *, const FT *, size_t, size_t, const unsigned *, void *, void *, annb_stream) {
   fatal_config("fp16 screen in the double build");
 }
 #endif
@@ -753,10 +754,10 @@ extern "C" void annb_gather_rows_screen(const FT *points, const u32 *order, size
 
 // fp16 copy of the points in original order (the screened supercharge reads it)
 extern "C" void annb_screen_prep_points(const FT *points, const FT *mean, size_t n, size_t d,
-                                        const unsigned *scale_bits, void *points16, annb_stream stream) {
+                                        const unsigned *scale_bits, void *points16, void *nrm, annb_stream stream) {
   if (d % 4 || d / 4 > 32 || ((d / 4) & (d / 4 - 1))) fatal_config("annb_screen_prep_points: d must be 4..128, a power of two");
   screen_prep_kernel<<<grid_for(n * (d / 4), 256), 256, 0, stream>>>(points, NULL, NULL, mean, n, (int)d, scale_bits,
-                                                                    (unsigned short *)points16, NULL);
+                                                                    (unsigned short *)points16, (float2 *)nrm);
   LAUNCH_CHECK("screen_prep_points");
 }
 

@@ -256,6 +256,187 @@ hash_points_reg_kernel(const FT *__restrict__ points, const FT *__restrict__ mea
   }
 }
 
+// Second register variant (needs the tables on the host).  Differences to the kernel above:
+//  * the per-try tables live in CONSTANT memory, re-written per launch: the index streams are
+//    uniform across the warp, so they come through the constant cache instead of the LSU;
+//  * the centred tile P is never copied per try: a "before" plane writes its two results to two
+//    fresh patch rows behind the tile, and the host resolves, for every later read (following
+//    planes, the sub-permutation gather), which row currently holds a coordinate;
+//  * W holds the transformed row for the data-dependent reads after the butterflies only.
+// Same operations in the same order on the same values: the hashes are bit-identical.
+struct HashOp { unsigned short a, b; };                       // rows read by a plane
+static constexpr int VE = 16 / sizeof(FT);                    // elements per 16-byte vector
+struct __align__(16) HashVec { FT x[VE]; };
+static const int HT_GSRC = 8192, HT_OPS = 1024, HT_PICK = 2048;
+__constant__ unsigned short c_hash_gsrc[HT_GSRC];             // [try][d_max]  row of P feeding z[y], 0xffff = zero
+__constant__ HashOp c_hash_ops[HT_OPS];                       // [try][planes] before (rows of P) then after (rows of W)
+__constant__ FT c_hash_cs[2 * HT_OPS];                        // [try][planes][cos, sin]
+__constant__ unsigned short c_hash_pick[HT_PICK];             // [try][d_short]
+
+template <int DM, int TP>
+__global__ void __launch_bounds__(TP)
+hash_points_const_kernel(const FT *__restrict__ points, const FT *__restrict__ mean, size_t n, int d,
+                         int planes_b, int planes_all, int ds, int tries, FT inv_sqrt2,
+                         u32 *__restrict__ hash) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int LD = TP + 1;
+  constexpr int LEVELS = DM == 16 ? 4 : DM == 32 ? 5 : DM == 64 ? 6 : 7;
+  FT *P = reinterpret_cast<FT *>(smem_raw);                   // [d + 2*planes_b][LD]
+  FT *W = P + (size_t)(d + 2 * planes_b) * LD;                // [DM][LD]
+  const int tid = threadIdx.x;
+  const size_t tiles = (n + TP - 1) / TP;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const size_t p0 = tile * TP;
+    const size_t rows = (n - p0 < (size_t)TP) ? n - p0 : (size_t)TP;
+    __syncthreads();
+    if ((d & (VE - 1)) == 0) {
+      // the tile is one contiguous run of rows: 16-byte loads, four per thread in flight (the
+      // pass is bound by this read of the points, so bytes in flight are what counts), then the
+      // centred values go to the transposed tile (compute.cl:44-49)
+      const int vpr = d / VE;                                  // vectors per row
+      const int total = (int)rows * vpr;
+      const HashVec *src = reinterpret_cast<const HashVec *>(points + p0 * (size_t)d);
+      const HashVec *mu = reinterpret_cast<const HashVec *>(mean);
+      for (int e0 = tid; e0 < total; e0 += 4 * TP) {
+        HashVec v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (e0 + u * TP < total) v[u] = src[e0 + u * TP];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int e = e0 + u * TP;
+          if (e < total) {
+            const int r = e / vpr, cv = e - r * vpr;
+            const HashVec m = mu[cv];
+#pragma unroll
+            for (int j = 0; j < VE; j++) P[(cv * VE + j) * LD + r] = v[u].x[j] - m.x[j];
+          }
+        }
+      }
+    } else {
+      for (size_t r = tid >> 5; r < rows; r += TP / 32) {
+        const FT *src = points + (p0 + r) * (size_t)d;
+        for (int c = tid & 31; c < d; c += 32) P[c * LD + r] = src[c] - mean[c];
+      }
+    }
+    __syncthreads();
+    if ((size_t)tid >= rows) continue;
+    for (int tr = 0; tr < tries; tr++) {
+      const HashOp *ops = c_hash_ops + tr * planes_all;
+      const FT *cs = c_hash_cs + 2 * tr * planes_all;
+      for (int q = 0; q < planes_b; q++) {                     // compute.cl:55-68
+        const FT c = cs[2 * q], sn = cs[2 * q + 1];
+        const FT a = P[ops[q].a * LD + tid], b = P[ops[q].b * LD + tid];
+        P[(d + 2 * q) * LD + tid] = a * c - b * sn;
+        P[(d + 2 * q + 1) * LD + tid] = a * sn + b * c;
+      }
+      FT z[DM];
+      const unsigned short *gsrc = c_hash_gsrc + tr * DM;
+#pragma unroll
+      for (int y = 0; y < DM; y++) {                           // compute.cl:77-85
+        const unsigned src = gsrc[y];
+        z[y] = src != 0xffffu ? P[src * LD + tid] : (FT)0;
+      }
+#pragma unroll
+      for (int lev = 0; lev < LEVELS; lev++) {                 // compute.cl:101-122
+#pragma unroll
+        for (int w = 0; w < DM / 2; w++) {
+          const int hi_part = (w >> lev) << lev, lo_part = w ^ hi_part;
+          const int ia = (hi_part << 1) | lo_part, ib = ia | (1 << lev);
+          FT a = z[ia], b = z[ib];
+          FT sm = a + b, df = a - b;
+          if (lev & 1) { sm *= (FT)0.5; df *= (FT)0.5; }
+          if (lev == 0 && (LEVELS & 1)) { sm *= inv_sqrt2; df *= inv_sqrt2; }
+          z[ia] = sm;
+          z[ib] = df;
+        }
+      }
+#pragma unroll
+      for (int y = 0; y < DM; y++) W[y * LD + tid] = z[y];
+      for (int q = planes_b; q < planes_all; q++) {
+        const FT c = cs[2 * q], sn = cs[2 * q + 1];
+        const int i = ops[q].a, j = ops[q].b;
+        const FT a = W[i * LD + tid], b = W[j * LD + tid];
+        W[i * LD + tid] = a * c - b * sn;
+        W[j * LD + tid] = a * sn + b * c;
+      }
+      const unsigned short *pick = c_hash_pick + tr * ds;
+      u32 h = 0;
+      for (int i = 0; i < ds; i++) h = (h << 1) | sign_bit(W[pick[i] * LD + tid]);
+      hash[(size_t)tr * n + p0 + tid] = h;
+    }
+  }
+}
+
+// tries are hashed in batches whose tables fit the constant arrays (one batch in every BASELINE
+// configuration); returns false when the shape does not fit this kernel at all
+template <int DM>
+static bool launch_hash_const(const FT *points, const FT *mean, const annb_transform_desc *t, u32 *hash,
+                              annb_stream stream) {
+  constexpr int TP = 128;
+  const size_t d = t->d, ds = t->d_short;
+  const size_t planes_b = t->rots_before * t->rot_len_before;
+  const size_t planes_all = planes_b + t->rots_after * t->rot_len_after;
+  if (!t->host_perm_b || !t->host_pick || (planes_all && (!t->host_plane_idx || !t->host_plane_cs))) return false;
+  const size_t smem = (d + 2 * planes_b + DM) * (size_t)(TP + 1) * sizeof(FT);
+  if (smem > 200 * 1024 || d + 2 * planes_b >= 0xffff || planes_all > (size_t)HT_OPS || ds > (size_t)HT_PICK) return false;
+  size_t batch = t->tries;
+  while (batch > 1 && (batch * DM > (size_t)HT_GSRC || batch * planes_all > (size_t)HT_OPS || batch * ds > (size_t)HT_PICK)) batch--;
+  static bool configured = false;
+  if (!configured) {
+    RT_CHECK(cudaFuncSetAttribute(hash_points_const_kernel<DM, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  static unsigned short *h_gsrc = NULL, *h_pick = NULL;
+  static HashOp *h_ops = NULL;
+  static FT *h_cs = NULL;
+  static unsigned *latest = NULL;
+  static size_t latest_cap = 0;
+  if (!h_gsrc) {                                               // pinned: the async copies below read them later
+    RT_CHECK(cudaMallocHost((void **)&h_gsrc, sizeof(unsigned short) * HT_GSRC));
+    RT_CHECK(cudaMallocHost((void **)&h_pick, sizeof(unsigned short) * HT_PICK));
+    RT_CHECK(cudaMallocHost((void **)&h_ops, sizeof(HashOp) * HT_OPS));
+    RT_CHECK(cudaMallocHost((void **)&h_cs, sizeof(FT) * 2 * HT_OPS));
+  }
+  if (d > latest_cap) { free(latest); latest = (unsigned *)malloc(sizeof(unsigned) * d); latest_cap = d; }
+  const size_t tiles = (t->n + TP - 1) / TP;
+  const unsigned grid = (unsigned)(tiles < 148 * 8 ? tiles : 148 * 8);
+  for (size_t t0 = 0; t0 < (size_t)t->tries; t0 += batch) {
+    const size_t nb = (size_t)t->tries - t0 < batch ? (size_t)t->tries - t0 : batch;
+    if (t0) RT_CHECK(cudaStreamSynchronize(stream));           // the staging arrays are about to be rewritten
+    for (size_t j = 0; j < nb; j++) {
+      const size_t tr = t0 + j;
+      for (size_t c = 0; c < d; c++) latest[c] = (unsigned)c;  // row of P holding coordinate c right now
+      for (size_t q = 0; q < planes_all; q++) {
+        const u32 i = t->host_plane_idx[(tr * planes_all + q) * 2], jj = t->host_plane_idx[(tr * planes_all + q) * 2 + 1];
+        HashOp &o = h_ops[j * planes_all + q];
+        if (q < planes_b) {
+          o.a = (unsigned short)latest[i]; o.b = (unsigned short)latest[jj];
+          latest[i] = (unsigned)(d + 2 * q); latest[jj] = (unsigned)(d + 2 * q + 1);
+        } else {
+          o.a = (unsigned short)i; o.b = (unsigned short)jj;
+        }
+        h_cs[2 * (j * planes_all + q)] = t->host_plane_cs[(tr * planes_all + q) * 2];
+        h_cs[2 * (j * planes_all + q) + 1] = t->host_plane_cs[(tr * planes_all + q) * 2 + 1];
+      }
+      for (size_t y = 0; y < (size_t)DM; y++) {
+        const u32 src = t->host_perm_b[tr * DM + y];
+        h_gsrc[j * DM + y] = src < d ? (unsigned short)latest[src] : (unsigned short)0xffff;
+      }
+      for (size_t i = 0; i < ds; i++) h_pick[j * ds + i] = (unsigned short)t->host_pick[tr * ds + i];
+    }
+    RT_CHECK(cudaMemcpyToSymbolAsync(c_hash_gsrc, h_gsrc, sizeof(unsigned short) * nb * DM, 0, cudaMemcpyHostToDevice, stream));
+    if (ds) RT_CHECK(cudaMemcpyToSymbolAsync(c_hash_pick, h_pick, sizeof(unsigned short) * nb * ds, 0, cudaMemcpyHostToDevice, stream));
+    if (planes_all) {
+      RT_CHECK(cudaMemcpyToSymbolAsync(c_hash_ops, h_ops, sizeof(HashOp) * nb * planes_all, 0, cudaMemcpyHostToDevice, stream));
+      RT_CHECK(cudaMemcpyToSymbolAsync(c_hash_cs, h_cs, sizeof(FT) * 2 * nb * planes_all, 0, cudaMemcpyHostToDevice, stream));
+    }
+    hash_points_const_kernel<DM, TP><<<grid, TP, smem, stream>>>(points, mean, t->n, (int)d, (int)planes_b, (int)planes_all,
+                                                                (int)ds, (int)nb, t->inv_sqrt2, hash + t0 * t->n);
+  }
+  return true;
+}
+
 template <int DM>
 static bool launch_hash_reg(const FT *points, const FT *mean, const annb_transform_desc *t, u32 *hash,
                             annb_stream stream) {
@@ -291,6 +472,19 @@ extern "C" void annb_hash_points(const FT *points, const FT *mean, const annb_tr
   {
     const char *off = getenv("ANN_B200_NO_REG_HASH");
     bool done = false;
+    const char *offc = getenv("ANN_B200_NO_CONST_HASH");
+    if (!(off && *off && *off != '0') && !(offc && *offc && *offc != '0')) {
+      switch (t->d_max) {
+        case 16: done = launch_hash_const<16>(points, mean, t, hash, stream); break;
+        case 32: done = launch_hash_const<32>(points, mean, t, hash, stream); break;
+        case 64: done = launch_hash_const<64>(points, mean, t, hash, stream); break;
+#ifdef USE_FLOAT
+        case 128: done = launch_hash_const<128>(points, mean, t, hash, stream); break;
+#endif
+        default: break;
+      }
+      if (done) { LAUNCH_CHECK("hash_points_const"); return; }
+    }
     if (!(off && *off && *off != '0')) {
       switch (t->d_max) {
         case 16: done = launch_hash_reg<16>(points, mean, t, hash, stream); break;
@@ -506,18 +700,46 @@ extern "C" void annb_gather_rows(const FT *points, const u32 *order, size_t n, s
   LAUNCH_CHECK("gather_rows");
 }
 
+template <typename CELL>
 __global__ void export_table_kernel(const u32 *__restrict__ offset, const u32 *__restrict__ order,
-                                    size_t n, size_t buckets, size_t tmax, size_t *table) {
+                                    size_t n, size_t buckets, size_t tmax, CELL *table) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= buckets * tmax) return;
   size_t b = e / tmax, z = e - b * tmax;
   u32 beg = offset[b], cnt = offset[b + 1] - beg;
-  table[e] = z < cnt ? (size_t)order[beg + z] : n;
+  table[e] = z < cnt ? (CELL)order[beg + z] : (CELL)n;
 }
 
 extern "C" void annb_export_table(const u32 *offset, const u32 *order, size_t n, size_t buckets,
                                   size_t tmax, size_t *table, annb_stream stream) {
-  export_table_kernel<<<grid_for(buckets * tmax, 256), 256, 0, stream>>>(offset, order, n, buckets, tmax, table);
+  export_table_kernel<size_t><<<grid_for(buckets * tmax, 256), 256, 0, stream>>>(offset, order, n, buckets, tmax, table);
   LAUNCH_CHECK("export_table");
+}
+
+extern "C" void annb_export_table32(const u32 *offset, const u32 *order, size_t n, size_t buckets,
+                                    size_t tmax, u32 *table, annb_stream stream) {
+  export_table_kernel<u32><<<grid_for(buckets * tmax, 256), 256, 0, stream>>>(offset, order, n, buckets, tmax, table);
+  LAUNCH_CHECK("export_table32");
+}
+
+// largest bucket of a try without building its table: histogram + maximum
+__global__ void max_count_kernel(const u32 *__restrict__ count, size_t buckets, u32 *tmax) {
+  u32 mx = 0;
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < buckets; b += (size_t)gridDim.x * blockDim.x)
+    mx = max(mx, count[b]);
+  mx = __reduce_max_sync(FULL, mx);
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(tmax, mx);
+}
+
+extern "C" void annb_bucket_max(const u32 *hash, size_t n, size_t buckets, u32 *count, u32 *tmax,
+                                annb_stream stream) {
+  RT_CHECK(cudaMemsetAsync(count, 0, buckets * sizeof(u32), stream));
+  RT_CHECK(cudaMemsetAsync(tmax, 0, sizeof(u32), stream));
+  histogram_kernel<<<grid_for(n, 256), 256, 0, stream>>>(hash, n, count);
+  LAUNCH_CHECK("histogram");
+  unsigned grid = grid_for(buckets, 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  max_count_kernel<<<grid, 256, 0, stream>>>(count, buckets, tmax);
+  LAUNCH_CHECK("max_count");
 }
 

@@ -78,6 +78,10 @@ struct QueryTables {
   u32 offset[64];
   int tries;
   unsigned long long len, prefix;
+  // hash of (query x, try t) = sign[t * s_try + x * s_row].  The reference writes the buffer as
+  // [x][try] and reads it as [try][x] (alg.c:474-499): s_try = ycnt, s_row = 1 reproduces that;
+  // s_try = 1, s_row = tries is the corrected read (ANN_B200_QUERY_LAYOUT=fixed, opt-in)
+  size_t s_try, s_row;
 };
 
 template <int E, int R>
@@ -102,7 +106,7 @@ query_rows_kernel(const FT *__restrict__ y, const FT *__restrict__ points, Query
   bool any_inf = false, tie = false, done = false;
 
   for (int t = 0; t < q.tries && !done; t++) {
-    const u32 h = sign[(size_t)t * ycnt + x];
+    const u32 h = sign[(size_t)t * q.s_try + x * q.s_row];
     const u32 w = q.width[t];
     for (int f = 0; f <= d_short; f++) {
       unsigned long long col = (unsigned long long)(d_short + 1) * q.offset[t] + (unsigned long long)f * w;
@@ -146,6 +150,136 @@ query_rows_kernel(const FT *__restrict__ y, const FT *__restrict__ points, Query
   if (tie && lane == 0) tie_report(ties, (u32)x);
 }
 
+// Fast path (float, d in {16,32,64,128}, k <= 32): query_rows_kernel measures one candidate at a
+// time (a dependent id load, then a dependent row load per candidate), which leaves the warp
+// waiting on memory.  Here the ids of the row's segments are collected in a small per-warp
+// buffer (coalesced loads from the tables, pads and the query itself dropped) and measured
+// 2*CPR at a time: d/8 lanes per candidate, lane g holding coordinates 4g..4g+3 and
+// d/2+4g..d/2+4g+3 (two 16-byte loads, whole 128-byte lines per instruction), the reference's
+// summation tree as in supercharge_screen_kernel.  Same candidates, same tree, same list rules
+// as the kernel above — only the order in which candidates are offered differs, and that order
+// only matters in rows with exact ties, which both kernels hand to the literal kernel.
+#ifdef USE_FLOAT
+static constexpr int QBUF = 192;                                  // buffered candidate ids per warp
+
+template <int D>
+__global__ void __launch_bounds__(256)
+query_rows_fast_kernel(const float *__restrict__ y, const float *__restrict__ points, QueryTables q,
+                       const u32 *__restrict__ sign, size_t n,
+                       size_t ycnt, int d_short, int k, int exclude_self, u32 *__restrict__ list_ids,
+                       float *__restrict__ list_dist, TieList ties) {
+  constexpr int LPC = D / 8, CPR = 32 / LPC;
+  __shared__ u32 s_buf[8][QBUF];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  size_t x = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (x >= ycnt) return;
+  u32 *buf = s_buf[wib];
+  const u32 sentinel = (u32)n;
+  const float inf = ft_inf();
+  const int g = lane & (LPC - 1), grp = lane / LPC;
+  const float4 qa = *reinterpret_cast<const float4 *>(y + x * (size_t)D + 4 * g);
+  const float4 qb = *reinterpret_cast<const float4 *>(y + x * (size_t)D + D / 2 + 4 * g);
+  WarpList<1> best;
+  best.clear(sentinel);
+  float tau = inf, max_v = -inf;
+  u32 max_id = sentinel, corner_id = sentinel;
+  bool any_inf = false, tie = false, done = false;
+  int cnt = 0;
+
+  auto flush = [&]() {
+    __syncwarp();
+    for (int base = 0; base < cnt; base += 2 * CPR) {
+      u32 cid[2];
+      float dist[2];
+      float4 ca[2], cb[2];
+#pragma unroll
+      for (int h2 = 0; h2 < 2; h2++) {
+        const int mine = base + CPR * h2 + grp;
+        cid[h2] = buf[mine < cnt ? mine : base];
+        const float *crow = points + (size_t)cid[h2] * D;
+        ca[h2] = *reinterpret_cast<const float4 *>(crow + 4 * g);
+        cb[h2] = *reinterpret_cast<const float4 *>(crow + D / 2 + 4 * g);
+      }
+#pragma unroll
+      for (int h2 = 0; h2 < 2; h2++) {
+        float m[4];
+        {
+          float d0 = qa.x - ca[h2].x, d1 = qa.y - ca[h2].y, d2 = qa.z - ca[h2].z, d3 = qa.w - ca[h2].w;
+          float e0 = qb.x - cb[h2].x, e1 = qb.y - cb[h2].y, e2 = qb.z - cb[h2].z, e3 = qb.w - cb[h2].w;
+          m[0] = d0 * d0 + e0 * e0; m[1] = d1 * d1 + e1 * e1;
+          m[2] = d2 * d2 + e2 * e2; m[3] = d3 * d3 + e3 * e3;
+        }
+#pragma unroll
+        for (int o = LPC / 2; o >= 1; o >>= 1) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) m[j] = m[j] + __shfl_xor_sync(FULL, m[j], o);
+        }
+        const float tt = (m[0] + m[2]) + (m[1] + m[3]);
+        const bool live = base + CPR * h2 + grp < cnt;
+        dist[h2] = live ? tt : inf;
+        if (live && tt > max_v) { max_v = tt; max_id = cid[h2]; }     // lane-local, reduced at the end
+      }
+      if (__any_sync(FULL, dist[0] <= tau || dist[1] <= tau)) {
+#pragma unroll
+        for (int h2 = 0; h2 < 2; h2++)
+          for (int i = 0; i < CPR; i++) {
+            float vn = __shfl_sync(FULL, dist[h2], LPC * i);
+            u32 idn = __shfl_sync(FULL, cid[h2], LPC * i);
+            if (vn != inf) consider<1>(best, tau, vn, idn, k, sentinel, lane, tie);
+          }
+      }
+    }
+    cnt = 0;
+    __syncwarp();
+  };
+
+  for (int t = 0; t < q.tries && !done; t++) {
+    const u32 h = sign[(size_t)t * q.s_try + x * q.s_row];
+    const u32 w = q.width[t];
+    for (int f = 0; f <= d_short; f++) {
+      unsigned long long col = (unsigned long long)(d_short + 1) * q.offset[t] + (unsigned long long)f * w;
+      const u32 *row = q.tab[t] + (size_t)(h ^ (f ? (1u << (f - 1)) : 0u)) * w;
+      if (col >= q.prefix) {
+        if (col == q.prefix && w) corner_id = row[0];
+        done = true;
+        break;
+      }
+      unsigned long long room = q.prefix - col;
+      u32 take = w < room ? w : (u32)room;
+      if (take < w) { corner_id = row[take]; done = true; }
+      for (u32 z0 = 0; z0 < take; z0 += 32) {
+        const u32 z = z0 + lane;
+        const u32 id = z < take ? row[z] : sentinel;
+        // pads fill the tail of a table row, so the real ids are a prefix of it
+        const unsigned real = __ballot_sync(FULL, z < take && id < sentinel);
+        if (__ballot_sync(FULL, z < take && id >= sentinel)) any_inf = true;
+        const bool self = exclude_self && id == (u32)x;
+        if (__ballot_sync(FULL, (real >> lane & 1) && self)) any_inf = true;
+        const unsigned keep = __ballot_sync(FULL, (real >> lane & 1) && !self);
+        if (keep >> lane & 1) buf[cnt + __popc(keep & ((1u << lane) - 1))] = id;
+        cnt += __popc(keep);
+        if (cnt > QBUF - 32) flush();
+        if (real != (z0 + 32 <= take ? 0xffffffffu : ((1u << (take - z0)) - 1u))) break;   // a pad was seen
+      }
+      if (done) break;
+    }
+  }
+  flush();
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    float ov = __shfl_xor_sync(FULL, max_v, o);
+    u32 oi = __shfl_xor_sync(FULL, max_id, o);
+    if (ov > max_v || (ov == max_v && oi < max_id)) { max_v = ov; max_id = oi; }
+  }
+  if (q.prefix < q.len && !any_inf && corner_id == max_id) best.remove(corner_id, sentinel, lane);
+  if (lane < k) {
+    list_ids[x * (size_t)k + lane] = best.id[0];
+    list_dist[x * (size_t)k + lane] = best.v[0];
+  }
+  if (tie && lane == 0) tie_report(ties, (u32)x);
+}
+#endif
+
 // literal row of a reported query: every column, the reference's network, first k out;
 // one CTA per row
 template <int E>
@@ -177,7 +311,7 @@ query_literal_kernel(const FT *__restrict__ y, const FT *__restrict__ points, Qu
     if (tid == 0) s_live = 0;
     __syncthreads();
     for (int t = 0; t < q.tries; t++) {
-      const u32 h = sign[(size_t)t * ycnt + x];
+      const u32 h = sign[(size_t)t * q.s_try + x * q.s_row];
       const u32 w = q.width[t];
       const size_t cols = (size_t)(d_short + 1) * w, col0 = (size_t)(d_short + 1) * q.offset[t];
       for (size_t c = tid; c < cols; c += blockDim.x) {
@@ -208,18 +342,34 @@ static void launch_query_rows(int regs, size_t smem, annb_stream stream, const F
                               int d_short, int k, int ex, u32 *ids, FT *dist, const LiteralScratch &ls,
                               int *status) {
   dim3 block(256), grid(grid_for(ycnt * 32, 256));
+  bool fast = false;
+#ifdef USE_FLOAT
+  {
+    const char *off = getenv("ANN_B200_NO_FAST_QUERY");
+    if (!(off && *off && *off != '0') && k <= 32 && (d == 16 || d == 32 || d == 64 || d == 128)) {
+      switch (d) {
+        case 16: query_rows_fast_kernel<16><<<grid, block, 0, stream>>>(y, points, q, sign, n, ycnt, d_short, k, ex, ids, dist, ls.list); break;
+        case 32: query_rows_fast_kernel<32><<<grid, block, 0, stream>>>(y, points, q, sign, n, ycnt, d_short, k, ex, ids, dist, ls.list); break;
+        case 64: query_rows_fast_kernel<64><<<grid, block, 0, stream>>>(y, points, q, sign, n, ycnt, d_short, k, ex, ids, dist, ls.list); break;
+        default: query_rows_fast_kernel<128><<<grid, block, 0, stream>>>(y, points, q, sign, n, ycnt, d_short, k, ex, ids, dist, ls.list); break;
+      }
+      fast = true;
+    }
+  }
+#endif
 #define QR_CASE(R)                                                                                \
   {                                                                                               \
     if (smem > 48 * 1024)                                                                         \
       RT_CHECK(cudaFuncSetAttribute(query_rows_kernel<E, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     query_rows_kernel<E, R><<<grid, block, smem, stream>>>(y, points, q, sign, n, ycnt, d, d_short, k, ex, ids, dist, ls.list); \
   }
-  switch (regs) {
-    case 1: QR_CASE(1) break;
-    case 2: QR_CASE(2) break;
-    case 4: QR_CASE(4) break;
-    default: QR_CASE(8) break;
-  }
+  if (!fast)
+    switch (regs) {
+      case 1: QR_CASE(1) break;
+      case 2: QR_CASE(2) break;
+      case 4: QR_CASE(4) break;
+      default: QR_CASE(8) break;
+    }
 #undef QR_CASE
   LAUNCH_CHECK("query_rows");
   if (smem > 48 * 1024)
@@ -244,6 +394,13 @@ extern "C" void annb_query_rows(const FT *y, const FT *points, const u32 *const 
     q.width[t] = (u32)par_maxes[t];
     q.offset[t] = (u32)off;
     off += par_maxes[t];
+  }
+  {
+    // opt-in corrected read of the sign buffer; the default reproduces the reference (bug included)
+    const char *lay = getenv("ANN_B200_QUERY_LAYOUT");
+    const bool fixed = lay && (lay[0] == 'f' || lay[0] == 'F');
+    q.s_try = fixed ? 1 : ycnt;
+    q.s_row = fixed ? (size_t)tries : 1;
   }
   q.len = off * (d_short + 1);
   if (q.len < 16) fatal_config("query candidate rows shorter than 16 slots");

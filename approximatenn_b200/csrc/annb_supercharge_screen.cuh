@@ -2,22 +2,20 @@
 //
 // supercharge_fast_kernel gathers every candidate's fp32 row (256 B at d = 64, as 32-byte pieces
 // of eight different 128-byte lines per load instruction) although only a few per cent of the
-// k*k candidates can beat the row's current k-th best.  Here every candidate is bracketed first
-// from the fp16 copy of the points in ORIGINAL order (one 128-byte line per row at d = 64, read
-// by d/8 lanes with one 16-byte load each, i.e. whole lines per instruction), and only
-// candidates whose lower bound reaches tau0 = the row's k-th own distance get the exact tree.
-// tau only shrinks while the row is processed, so tau0 is conservative; whatever is reported
-// is computed by the exact tree (same operations, same order, same bits as the fast kernel).
+// k*k candidates can beat the row's current k-th best (cfg3: 10 of 235).  Here every candidate
+// is bracketed first from the fp16 copy of the points in ORIGINAL order, and only candidates
+// whose lower bound reaches tau0 = the row's k-th own distance get the exact tree.  tau only
+// shrinks while the row is processed, so tau0 is conservative; whatever is reported is computed
+// by the exact tree (same operations, same order, same bits as the fast kernel).
 //
-// Bracket (DESIGN.md "screened leaf" derives it; tests/test_screen_bounds.py replays it): with
-// c' = fp16((x - mean) * scale), D' = n2q + n2c - 2 q'.c' in fp32 and t = sq + sc,
-// |D - D'| <= t^2 for the exact path's value D in scaled units.  This kernel has no norm table:
-// n2 = sum c'^2 is accumulated from the row it has just loaded (FHFMA: fp16 x fp16 + fp32, one
-// instruction, products exact), and the norm bound is taken from it:
-//   ||c|| <= ||c'|| (1 + 2^-10) + sqrt(d) 2^-24   (fp16 rounding incl. subnormals)
-//   s' = sqrt(kappa) (sqrt(n2) (1 + 2^-9) + sqrt(d) 2^-13) >= sqrt(kappa) (||c|| (1 + 2^-12) + sqrt(d) 2^-14) = s,
-// the extra 2^-10 covering the rounding of n2 (<= d 2^-24 relative) and of sqrtf.  A larger t
-// only widens the bracket.
+// Bracket: the one of the screened S3 path (DESIGN.md "screened leaf" derives it,
+// tests/test_screen_bounds.py replays it): c' = fp16((x - mean) * scale), per row
+// (s, n2) = (sqrt(kappa) (||c|| (1 + 2^-12) + sqrt(d) 2^-14), sum c'^2) from the same preparation
+// kernel, D' = n2q + n2c - 2 q'.c' with the dot product on the tensor cores (mma.m16n8k16, fp16
+// in, fp32 accumulate), t = sq + sc, and |D - D'| <= t^2 for the exact path's value D in scaled
+// units.  One warp owns one row: all 16 rows of the A operand are the query, the B operand is
+// eight candidates, so after d/16 MMAs lane (g, t) holds the dot products of candidates 2t and
+// 2t+1 of the round — no shuffles, ~4 instructions per candidate.
 //
 // Prefix corner (alg.c:313-327 via rdups): it removes the id in slot P2 from the k best only if
 // that id is the largest entry of the prefix.  If at least one candidate was screened out it is
@@ -33,29 +31,18 @@ extern "C" void annb_supercharge_screen_stats(unsigned long long out[2], int res
   if (reset) cudaMemcpyToSymbol(s5_screen_stats_dev, z, sizeof z);
 }
 
-// dot += a . b and nn += b . b over the 8 fp16 values of two 16-byte pieces (FHFMA)
-__device__ __forceinline__ void half8_dot_norm(const uint4 &a, const uint4 &b, float &dot, float &nn) {
-  const unsigned as[4] = {a.x, a.y, a.z, a.w}, bs[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    asm("{\n\t.reg .f16 a0, a1, b0, b1;\n\t"
-        "mov.b32 {a0, a1}, %2;\n\tmov.b32 {b0, b1}, %3;\n\t"
-        "fma.rn.f32.f16 %0, a0, b0, %0;\n\tfma.rn.f32.f16 %0, a1, b1, %0;\n\t"
-        "fma.rn.f32.f16 %1, b0, b0, %1;\n\tfma.rn.f32.f16 %1, b1, b1, %1;\n\t}"
-        : "+f"(dot), "+f"(nn) : "r"(as[i]), "r"(bs[i]));
-  }
-}
-
 template <int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, D >= 128 ? 2 : 3)
 supercharge_screen_kernel(const float *__restrict__ points, const unsigned short *__restrict__ points16,
-                          const unsigned *__restrict__ scale_bits, const u32 *__restrict__ own_ids,
+                          const float2 *__restrict__ pnrm, const unsigned *__restrict__ scale_bits,
+                          const u32 *__restrict__ own_ids,
                           const float *__restrict__ own_dist, const u32 *__restrict__ graph, size_t n,
                           int k, size_t row_begin, size_t row_end, const u32 *__restrict__ row_perm,
                           u32 *__restrict__ out_ids, float *__restrict__ out_dist, TieList ties) {
-  constexpr int LPC = D / 8;                         // lanes per candidate: 16 bytes of fp16 / 32 bytes of fp32 each
-  constexpr int CPR = 32 / LPC;                      // candidates per round
-  constexpr int SR = 4;                              // screen rounds in flight
+  constexpr int LPC = D / 8;                         // exact tree: lanes per candidate, 32 bytes of fp32 each
+  constexpr int CPR = 32 / LPC;                      // exact tree: candidates per round
+  constexpr int KS = D / 16;                         // screen: k-steps (MMAs) per round of 8 candidates
+  constexpr int SR = D >= 128 ? 2 : 3;               // screen rounds in flight
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned s_stats[2];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -69,8 +56,7 @@ supercharge_screen_kernel(const float *__restrict__ points, const unsigned short
     const int wide = k * (k + 1);
     const int P2 = 1 << floor_log2_u((unsigned long long)wide);
     const int cand = P2 - k;
-    u32 *uniq = reinterpret_cast<u32 *>(smem_raw) + (size_t)wib * ((size_t)k * k);
-    const int g = lane & (LPC - 1), grp = lane / LPC;
+    u32 *uniq = reinterpret_cast<u32 *>(smem_raw) + (size_t)wib * (((size_t)k * k + 9) & ~(size_t)1);   // 8-byte aligned
 
     // scale of the fp16 copy (a power of two); outside a sane exponent range the screen passes
     // everything (the exact path's rounding is only relative away from underflow)
@@ -99,7 +85,7 @@ supercharge_screen_kernel(const float *__restrict__ points, const unsigned short
     for (int o = 16; o >= 1; o >>= 1) {
       float ov = __shfl_xor_sync(FULL, max_v, o);
       u32 oi = __shfl_xor_sync(FULL, max_id, o);
-      if (ov > max_v) { max_v = ov; max_id = oi; }
+      if (ov > max_v || (ov == max_v && oi < max_id)) { max_v = ov; max_id = oi; }   // uniform on ties
     }
     float tau = best.kth(k);
     const float tau0s = scale2 > 0.f ? tau * scale2 : inf;            // +inf stays +inf: everything passes
@@ -125,64 +111,68 @@ supercharge_screen_kernel(const float *__restrict__ points, const unsigned short
     tie = __any_sync(FULL, tie);
     __syncwarp();
 
-    // ---- the query: fp16 piece for the screen, fp32 pieces for the exact tree -----------------
-    const uint4 q16 = *reinterpret_cast<const uint4 *>(points16 + x * (size_t)D + 8 * g);
-    float qn2 = 0.f;
-    {
-      float dummy = 0.f;
-      half8_dot_norm(q16, q16, dummy, qn2);
-#pragma unroll
-      for (int o = LPC / 2; o >= 1; o >>= 1) qn2 += __shfl_xor_sync(FULL, qn2, o);
-    }
-    const float root_d = sqrtf((float)D);
-    const float sq = SCREEN_SQRT_KAPPA * (sqrtf(qn2) * (1.0f + 1.0f / 512.0f) + root_d * (1.0f / 8192.0f));
-    const float4 qa = *reinterpret_cast<const float4 *>(points + x * (size_t)D + 4 * g);
-    const float4 qb = *reinterpret_cast<const float4 *>(points + x * (size_t)D + D / 2 + 4 * g);
-
-    // ---- screen: CPR candidates per round, SR rounds in flight; survivors are compacted in
-    // place into uniq[0..V) (V never overtakes the round being evaluated) ----------------------
+    // ---- screen: rounds of 8 candidates, SR rounds in flight.  The list is padded to whole rounds
+    // with the row's own id (a valid row; dead by position).  Lane (g8, t4) loads its 16-byte
+    // pieces of candidate g8's fp16 row and, for the epilogue, the ids and (s, n2) of candidates
+    // 2*t4 and 2*t4+1, whose dot products the MMAs leave in its accumulators.  Survivors are
+    // compacted in place into uniq[0..V): every read of a round happens SR rounds before its
+    // survivors are written, and V never overtakes the round being evaluated. --------------------
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int U8 = (U + 7) & ~7;
+    if (lane < U8 - U) uniq[U + lane] = (u32)x;
+    __syncwarp();
+    ScreenRow<D> qr16;
+    qr16.load(points16 + x * (size_t)D, t4);
+    const float2 qn = pnrm[x];
     int V = 0;
     {
-      uint4 v[SR];
-      u32 cid[SR];
-      auto load = [&](int b, uint4 &vv, u32 &cc) {
-        const int mine = b + grp;
-        cc = uniq[mine < U ? mine : U - 1];
-        vv = *reinterpret_cast<const uint4 *>(points16 + (size_t)cc * D + 8 * g);
+      ScreenRow<D> rb[SR];
+      uint2 ab[SR];
+      float2 na[SR], nb[SR];
+      auto load = [&](int b, ScreenRow<D> &row, uint2 &pair, float2 &n0, float2 &n1) {
+        row.load(points16 + (size_t)uniq[b + g8] * D, t4);
+        pair = *reinterpret_cast<const uint2 *>(&uniq[b + 2 * t4]);
+        n0 = pnrm[pair.x];
+        n1 = pnrm[pair.y];
       };
-      auto eval = [&](int b, const uint4 &vv, u32 cc) {
-        float dot = 0.f, cn2 = 0.f;
-        half8_dot_norm(q16, vv, dot, cn2);
+      auto eval = [&](int b, const ScreenRow<D> &row, const uint2 &pair, const float2 &n0, const float2 &n1) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int o = LPC / 2; o >= 1; o >>= 1) {
-          dot += __shfl_xor_sync(FULL, dot, o);
-          cn2 += __shfl_xor_sync(FULL, cn2, o);
+        for (int ks = 0; ks < KS; ks++)
+          mma_f16_16816(c, qr16.r[2 * ks], qr16.r[2 * ks], qr16.r[2 * ks + 1], qr16.r[2 * ks + 1], row.r[2 * ks], row.r[2 * ks + 1]);
+        const float t0 = qn.x + n0.x, t1 = qn.x + n1.x;
+        const float lo0 = __fmaf_rn(-t0, t0, __fmaf_rn(-2.0f, c[0], qn.y + n0.y));
+        const float lo1 = __fmaf_rn(-t1, t1, __fmaf_rn(-2.0f, c[1], qn.y + n1.y));
+        const bool p0 = g8 == 0 && b + 2 * t4 < U && lo0 <= tau0s;
+        const bool p1 = g8 == 0 && b + 2 * t4 + 1 < U && lo1 <= tau0s;
+        const unsigned m0 = __ballot_sync(FULL, p0), m1 = __ballot_sync(FULL, p1);
+        if (m0 | m1) {
+          const unsigned lt = (1u << lane) - 1;
+          if (p0) uniq[V + __popc(m0 & lt)] = pair.x;
+          if (p1) uniq[V + __popc(m0) + __popc(m1 & lt)] = pair.y;
+          V += __popc(m0) + __popc(m1);
         }
-        const float sc = SCREEN_SQRT_KAPPA * (sqrtf(cn2) * (1.0f + 1.0f / 512.0f) + root_d * (1.0f / 8192.0f));
-        const float t = sq + sc;
-        const float lo = ((qn2 + cn2) - 2.0f * dot) - t * t;
-        const bool pass = (b + grp < U) && g == 0 && lo <= tau0s;
-        const unsigned m = __ballot_sync(FULL, pass);
-        if (pass) uniq[V + __popc(m & ((1u << lane) - 1))] = cc;
-        V += __popc(m);
       };
-      if (U > 0) {
 #pragma unroll
-        for (int r = 0; r < SR; r++)
-          if (r * CPR < U) load(r * CPR, v[r], cid[r]);
-        for (int base = 0; base < U; base += SR * CPR) {
+      for (int r = 0; r < SR; r++)
+        if (8 * r < U8) load(8 * r, rb[r], ab[r], na[r], nb[r]);
+      for (int base = 0; base < U8; base += 8 * SR) {
 #pragma unroll
-          for (int r = 0; r < SR; r++) {
-            const int b = base + r * CPR;
-            if (b < U) {
-              eval(b, v[r], cid[r]);
-              if (b + SR * CPR < U) load(b + SR * CPR, v[r], cid[r]);
-            }
+        for (int r = 0; r < SR; r++) {
+          const int b = base + 8 * r;
+          if (b < U8) {
+            eval(b, rb[r], ab[r], na[r], nb[r]);
+            if (b + 8 * SR < U8) load(b + 8 * SR, rb[r], ab[r], na[r], nb[r]);
           }
         }
       }
     }
     __syncwarp();
+
+    // ---- the query's fp32 pieces for the exact tree ---------------------------------------------
+    const int g = lane & (LPC - 1), grp = lane / LPC;
+    const float4 qa = *reinterpret_cast<const float4 *>(points + x * (size_t)D + 4 * g);
+    const float4 qb = *reinterpret_cast<const float4 *>(points + x * (size_t)D + D / 2 + 4 * g);
 
     // ---- exact tree for the survivors, two rounds of CPR candidates per iteration: lane g of a
     // candidate's LPC lanes holds coordinates 4g..4g+3 and d/2+4g..d/2+4g+3 (two 16-byte loads,
@@ -246,7 +236,7 @@ supercharge_screen_kernel(const float *__restrict__ points, const unsigned short
       for (int o = 16; o >= 1; o >>= 1) {
         float ov = __shfl_xor_sync(FULL, lmax_v, o);
         u32 oi = __shfl_xor_sync(FULL, lmax_id, o);
-        if (ov > lmax_v) { lmax_v = ov; lmax_id = oi; }
+        if (ov > lmax_v || (ov == lmax_v && oi < lmax_id)) { lmax_v = ov; lmax_id = oi; }   // uniform on ties
       }
       if (lmax_v > max_v) { max_v = lmax_v; max_id = lmax_id; }
       int c = P2 - k, j = c / k, z = c - j * k;

@@ -53,6 +53,12 @@ typedef struct {
   const ftype *plane_cs;
   const annb_u32 *perm_b;
   const annb_u32 *pick;
+  /* the same four tables in HOST memory (optional, all or none): with them the register kernel
+   * keeps the per-try tables in constant memory and never copies the tile per try             */
+  const annb_u32 *host_plane_idx;
+  const ftype *host_plane_cs;
+  const annb_u32 *host_perm_b;
+  const annb_u32 *host_pick;
 } annb_transform_desc;
 /* scratch: device workspace of annb_hash_scratch_bytes() bytes (may be NULL when 0)     */
 size_t annb_hash_scratch_bytes(const annb_transform_desc *t);
@@ -76,6 +82,14 @@ void annb_gather_rows(const ftype *points, const annb_u32 *order, size_t n, size
 /* padded table as save_t stores it (which_par[t], [buckets][tmax] size_t, pad = n)       */
 void annb_export_table(const annb_u32 *offset, const annb_u32 *order, size_t n, size_t buckets,
                        size_t tmax, size_t *table, annb_stream stream);
+
+/* the same table with 32-bit cells (the host widens them while the GPU goes on; the query
+ * cache keeps this form), and the largest bucket of a try without building its table (count:
+ * `buckets` scratch words) so that a caller can size every table before the tries run        */
+void annb_export_table32(const annb_u32 *offset, const annb_u32 *order, size_t n, size_t buckets,
+                         size_t tmax, annb_u32 *table, annb_stream stream);
+void annb_bucket_max(const annb_u32 *hash, size_t n, size_t buckets, annb_u32 *count,
+                     annb_u32 *tmax, annb_stream stream);
 
 /* ---- exact ties ------------------------------------------------------------------------
  * S3, S4 and S5 each run a fast kernel that keeps the k best per row, then redo — with the
@@ -146,14 +160,16 @@ void annb_merge_lists(const annb_u32 *lists_ids, const ftype *lists_dist, int n_
  * graph may be the merged ids themselves (precomp) or save->graph (query).
  * scratch: at least (row_end-row_begin) + 512 bytes plus room for literal rows.           */
 /* opts (may be NULL): extras of the precomp path, where the queries ARE the points.
- *   points16/scale_bits  fp16 copy of the points in original order (annb_screen_prep_points) and
- *                        its scale word: candidates are bracketed from it and only those that can
- *                        reach the row's k best are measured exactly (float, d in {16,32,64,128},
- *                        k <= 32; same rows bit for bit; ANN_B200_S5_SCREEN=0 switches it off)
+ *   points16/nrm/scale_bits  fp16 copy of the points in original order, its per-row (norm bound,
+ *                        squared fp16 norm) pairs (annb_screen_prep_points) and the scale word:
+ *                        candidates are bracketed from them and only those that can reach the
+ *                        row's k best are measured exactly (float, d in {16,32,64,128}, k <= 32;
+ *                        same rows bit for bit; ANN_B200_S5_SCREEN=0 switches it off)
  *   row_perm             a permutation of [row_begin, row_end) (indexed by row): the order in
  *                        which the rows are worked on (locality), NULL = ascending                */
 typedef struct {
   const void *points16;
+  const void *nrm;
   const unsigned *scale_bits;
   const annb_u32 *row_perm;
 } annb_supercharge_opts;
@@ -169,9 +185,9 @@ void annb_merge_thread_mode(int on);
 /* 1 if annb_supercharge will use points16 for this shape                                       */
 int annb_supercharge_screen_applies(size_t d, size_t k);
 /* fp16 copy of the points in ORIGINAL order for the screened supercharge: c' = fp16((x - mean)
- * * scale), scale from the word annb_screen_scale() wrote.  points16: n*d*2 bytes.              */
+ * * scale), scale from the word annb_screen_scale() wrote.  points16: n*d*2 bytes, nrm: n*8.    */
 void annb_screen_prep_points(const ftype *points, const ftype *mean, size_t n, size_t d,
-                             const unsigned *scale_bits, void *points16, annb_stream stream);
+                             const unsigned *scale_bits, void *points16, void *nrm, annb_stream stream);
 /* candidates the screened supercharge bracketed [0] and measured exactly [1] since the last reset */
 void annb_supercharge_screen_stats(unsigned long long out[2], int reset);
 
