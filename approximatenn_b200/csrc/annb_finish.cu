@@ -838,7 +838,7 @@ extern "C" void annb_supercharge(const FT *queries, const FT *points, const u32 
   // screened path: precomp only (the queries are the points, so their fp16 rows exist)
   if (opts && opts->points16 && opts->nrm && opts->scale_bits && exclude_self && queries == points &&
       annb_supercharge_screen_applies(d, k)) {
-    const size_t ssmem = ((k * k + 9) & ~(size_t)1) * sizeof(u32) * 8;
+    const size_t ssmem = (k * k + 16) * sizeof(u32) * 8;
     dim3 block(256), grid(grid_for(rows * 32, 256));
     const unsigned short *p16 = (const unsigned short *)opts->points16;
     const float2 *pn = (const float2 *)opts->nrm;

@@ -32,7 +32,7 @@ extern "C" void annb_supercharge_screen_stats(unsigned long long out[2], int res
 }
 
 template <int D>
-__global__ void __launch_bounds__(256, D >= 128 ? 2 : 3)
+__global__ void __launch_bounds__(256, D >= 128 ? 2 : 4)
 supercharge_screen_kernel(const float *__restrict__ points, const unsigned short *__restrict__ points16,
                           const float2 *__restrict__ pnrm, const unsigned *__restrict__ scale_bits,
                           const u32 *__restrict__ own_ids,
@@ -41,8 +41,7 @@ supercharge_screen_kernel(const float *__restrict__ points, const unsigned short
                           u32 *__restrict__ out_ids, float *__restrict__ out_dist, TieList ties) {
   constexpr int LPC = D / 8;                         // exact tree: lanes per candidate, 32 bytes of fp32 each
   constexpr int CPR = 32 / LPC;                      // exact tree: candidates per round
-  constexpr int KS = D / 16;                         // screen: k-steps (MMAs) per round of 8 candidates
-  constexpr int SR = D >= 128 ? 2 : 3;               // screen rounds in flight
+  constexpr int KS = D / 16;                         // screen: k-steps (MMAs) per round of 16 candidates
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned s_stats[2];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -56,7 +55,7 @@ supercharge_screen_kernel(const float *__restrict__ points, const unsigned short
     const int wide = k * (k + 1);
     const int P2 = 1 << floor_log2_u((unsigned long long)wide);
     const int cand = P2 - k;
-    u32 *uniq = reinterpret_cast<u32 *>(smem_raw) + (size_t)wib * (((size_t)k * k + 9) & ~(size_t)1);   // 8-byte aligned
+    u32 *uniq = reinterpret_cast<u32 *>(smem_raw) + (size_t)wib * ((size_t)k * k + 16);
 
     // scale of the fp16 copy (a power of two); outside a sane exponent range the screen passes
     // everything (the exact path's rounding is only relative away from underflow)
@@ -90,80 +89,85 @@ supercharge_screen_kernel(const float *__restrict__ points, const unsigned short
     float tau = best.kth(k);
     const float tau0s = scale2 > 0.f ? tau * scale2 : inf;            // +inf stays +inf: everything passes
 
-    // candidate ids -> uniq[0..U): pads and the point itself are dropped here (compute.cl:145)
+    // candidate ids -> uniq[0..U): pads and the point itself are dropped here (compute.cl:145).
+    // The loads of four batches are issued before any of them is consumed.
     int U = 0;
-    for (int base = 0; base < cand; base += 32) {
-      int c = base + lane;
-      int j = c < cand ? c / k : 0;
-      int z = c - j * k;
-      u32 oj = __shfl_sync(FULL, own_reg, j);
-      u32 cid = (c < cand && oj < sentinel) ? graph[(size_t)oj * k + z] : sentinel;
-      bool keep = false;
-      if (c < cand) {
-        if (cid >= sentinel || cid == (u32)x) any_inf = true;
-        else keep = true;
+    for (int base0 = 0; base0 < cand; base0 += 128) {
+      u32 cidv[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int c = base0 + 32 * u + lane;
+        const int j = c < cand ? c / k : 0;
+        const int z = c - j * k;
+        const u32 oj = __shfl_sync(FULL, own_reg, j);
+        cidv[u] = (c < cand && oj < sentinel) ? graph[(size_t)oj * k + z] : sentinel;
       }
-      unsigned m = __ballot_sync(FULL, keep);
-      if (keep) uniq[U + __popc(m & ((1u << lane) - 1))] = cid;
-      U += __popc(m);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int c = base0 + 32 * u + lane;
+        bool keep = false;
+        if (c < cand) {
+          if (cidv[u] >= sentinel || cidv[u] == (u32)x) any_inf = true;
+          else keep = true;
+        }
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (keep) uniq[U + __popc(m & ((1u << lane) - 1))] = cidv[u];
+        U += __popc(m);
+      }
     }
     any_inf = __any_sync(FULL, any_inf);
     tie = __any_sync(FULL, tie);
     __syncwarp();
 
-    // ---- screen: rounds of 8 candidates, SR rounds in flight.  The list is padded to whole rounds
-    // with the row's own id (a valid row; dead by position).  Lane (g8, t4) loads its 16-byte
-    // pieces of candidate g8's fp16 row and, for the epilogue, the ids and (s, n2) of candidates
-    // 2*t4 and 2*t4+1, whose dot products the MMAs leave in its accumulators.  Survivors are
-    // compacted in place into uniq[0..V): every read of a round happens SR rounds before its
-    // survivors are written, and V never overtakes the round being evaluated. --------------------
+    // ---- screen: rounds of 16 candidates, double buffered.  The list is padded to whole rounds
+    // with the row's own id (a valid row; dead by position).  The CANDIDATES are the A operand
+    // (16 rows) and the query is the B operand (its 8 columns all equal), so lane (g8, t4) loads
+    // its 16-byte pieces of the fp16 rows of candidates g8 and g8+8 of the round and finds their
+    // dot products with the query in accumulators 0 and 2 after d/16 MMAs.  Lanes t4 = 0 / 1
+    // finish candidate g8 / g8+8: one (s, n2) load, five flops, one vote per round.  Survivors
+    // are compacted in place into uniq[0..V): a round's ids are read one round before its
+    // survivors are written, and V never overtakes the round being evaluated. -------------------
     const int g8 = lane >> 2, t4 = lane & 3;
-    const int U8 = (U + 7) & ~7;
-    if (lane < U8 - U) uniq[U + lane] = (u32)x;
+    const int U16 = (U + 15) & ~15;
+    if (lane < U16 - U) uniq[U + lane] = (u32)x;
     __syncwarp();
     ScreenRow<D> qr16;
     qr16.load(points16 + x * (size_t)D, t4);
     const float2 qn = pnrm[x];
     int V = 0;
     {
-      ScreenRow<D> rb[SR];
-      uint2 ab[SR];
-      float2 na[SR], nb[SR];
-      auto load = [&](int b, ScreenRow<D> &row, uint2 &pair, float2 &n0, float2 &n1) {
-        row.load(points16 + (size_t)uniq[b + g8] * D, t4);
-        pair = *reinterpret_cast<const uint2 *>(&uniq[b + 2 * t4]);
-        n0 = pnrm[pair.x];
-        n1 = pnrm[pair.y];
+      auto load = [&](int b, ScreenRow<D> &r0, ScreenRow<D> &r1, u32 &ce, float2 &ne) {
+        const u32 c0 = uniq[b + g8], c1 = uniq[b + g8 + 8];
+        r0.load(points16 + (size_t)c0 * D, t4);
+        r1.load(points16 + (size_t)c1 * D, t4);
+        ce = (t4 & 1) ? c1 : c0;                                   // the candidate this lane finishes
+        ne = pnrm[ce];
       };
-      auto eval = [&](int b, const ScreenRow<D> &row, const uint2 &pair, const float2 &n0, const float2 &n1) {
+      auto eval = [&](int b, const ScreenRow<D> &r0, const ScreenRow<D> &r1, u32 ce, const float2 &ne) {
         float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ks = 0; ks < KS; ks++)
-          mma_f16_16816(c, qr16.r[2 * ks], qr16.r[2 * ks], qr16.r[2 * ks + 1], qr16.r[2 * ks + 1], row.r[2 * ks], row.r[2 * ks + 1]);
-        const float t0 = qn.x + n0.x, t1 = qn.x + n1.x;
-        const float lo0 = __fmaf_rn(-t0, t0, __fmaf_rn(-2.0f, c[0], qn.y + n0.y));
-        const float lo1 = __fmaf_rn(-t1, t1, __fmaf_rn(-2.0f, c[1], qn.y + n1.y));
-        const bool p0 = g8 == 0 && b + 2 * t4 < U && lo0 <= tau0s;
-        const bool p1 = g8 == 0 && b + 2 * t4 + 1 < U && lo1 <= tau0s;
-        const unsigned m0 = __ballot_sync(FULL, p0), m1 = __ballot_sync(FULL, p1);
-        if (m0 | m1) {
-          const unsigned lt = (1u << lane) - 1;
-          if (p0) uniq[V + __popc(m0 & lt)] = pair.x;
-          if (p1) uniq[V + __popc(m0) + __popc(m1 & lt)] = pair.y;
-          V += __popc(m0) + __popc(m1);
+          mma_f16_16816(c, r0.r[2 * ks], r1.r[2 * ks], r0.r[2 * ks + 1], r1.r[2 * ks + 1], qr16.r[2 * ks], qr16.r[2 * ks + 1]);
+        const float dot = (t4 & 1) ? c[2] : c[0];
+        const float t = qn.x + ne.x;
+        const float lo = __fmaf_rn(-t, t, __fmaf_rn(-2.0f, dot, qn.y + ne.y));
+        const bool pass = t4 < 2 && b + g8 + 8 * (t4 & 1) < U && lo <= tau0s;
+        const unsigned m = __ballot_sync(FULL, pass);
+        if (m) {
+          if (pass) uniq[V + __popc(m & ((1u << lane) - 1))] = ce;
+          V += __popc(m);
         }
       };
-#pragma unroll
-      for (int r = 0; r < SR; r++)
-        if (8 * r < U8) load(8 * r, rb[r], ab[r], na[r], nb[r]);
-      for (int base = 0; base < U8; base += 8 * SR) {
-#pragma unroll
-        for (int r = 0; r < SR; r++) {
-          const int b = base + 8 * r;
-          if (b < U8) {
-            eval(b, rb[r], ab[r], na[r], nb[r]);
-            if (b + 8 * SR < U8) load(b + 8 * SR, rb[r], ab[r], na[r], nb[r]);
-          }
+      ScreenRow<D> a0, a1, b0, b1;
+      u32 ca = 0, cb = 0;
+      float2 na = make_float2(0.f, 0.f), nb = na;
+      if (U16 > 0) load(0, a0, a1, ca, na);
+      for (int base = 0; base < U16; base += 32) {
+        if (base + 16 < U16) load(base + 16, b0, b1, cb, nb);
+        eval(base, a0, a1, ca, na);
+        if (base + 16 < U16) {
+          if (base + 32 < U16) load(base + 32, a0, a1, ca, na);
+          eval(base + 16, b0, b1, cb, nb);
         }
       }
     }
