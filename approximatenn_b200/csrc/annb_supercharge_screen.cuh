@@ -41,7 +41,7 @@ supercharge_screen_kernel(const float *__restrict__ points, const unsigned short
                           u32 *__restrict__ out_ids, float *__restrict__ out_dist, TieList ties) {
   constexpr int LPC = D / 8;                         // exact tree: lanes per candidate, 32 bytes of fp32 each
   constexpr int CPR = 32 / LPC;                      // exact tree: candidates per round
-  constexpr int KS = D / 16;                         // screen: k-steps (MMAs) per round of 16 candidates
+  constexpr int KS2 = D >= 32 ? D / 32 : 1;          // screen: MMAs per group of 8 candidates (32 coordinates each)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned s_stats[2];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -119,55 +119,80 @@ supercharge_screen_kernel(const float *__restrict__ points, const unsigned short
     tie = __any_sync(FULL, tie);
     __syncwarp();
 
-    // ---- screen: rounds of 16 candidates, double buffered.  The list is padded to whole rounds
-    // with the row's own id (a valid row; dead by position).  The CANDIDATES are the A operand
-    // (16 rows) and the query is the B operand (its 8 columns all equal), so lane (g8, t4) loads
-    // its 16-byte pieces of the fp16 rows of candidates g8 and g8+8 of the round and finds their
-    // dot products with the query in accumulators 0 and 2 after d/16 MMAs.  Lanes t4 = 0 / 1
-    // finish candidate g8 / g8+8: one (s, n2) load, five flops, one vote per round.  Survivors
-    // are compacted in place into uniq[0..V): a round's ids are read one round before its
+    // ---- screen: rounds of 16 candidates.  The list is padded to whole rounds with the row's own
+    // id (a valid row; dead by position).  Operand layout (no register shuffling at all): lane
+    // (g8, t4) loads the 16 bytes at 64 v + 16 t4 of candidate g8's fp16 row straight into the four
+    // A registers of k-step v.  The hardware reads them as (row g8, k 2t..2t+1), (row g8+8, same
+    // k), (row g8, k 2t+8..), (row g8+8, ...), i.e. MMA rows g8 and g8+8 are the SAME candidate
+    // with the words (x, z) and (y, w) of every 16-byte piece.  The B operand carries the query's
+    // (x, z) words in its even columns and its (y, w) words in its odd columns, so
+    // D[g8][even] + D[g8+8][odd] = accumulator 0 + accumulator 3 of every lane of the quad is the
+    // full dot product.  Two such groups (candidates g8 and g8+8 of the round) per round; lanes
+    // t4 = 0 / 1 finish one candidate each: one (s, n2) load, five flops, one vote.  Survivors are
+    // compacted in place into uniq[0..V): a round's ids are read before the previous round's
     // survivors are written, and V never overtakes the round being evaluated. -------------------
     const int g8 = lane >> 2, t4 = lane & 3;
     const int U16 = (U + 15) & ~15;
     if (lane < U16 - U) uniq[U + lane] = (u32)x;
     __syncwarp();
-    ScreenRow<D> qr16;
-    qr16.load(points16 + x * (size_t)D, t4);
+    u32 qw[KS2][2];                                              // B operand: this lane's query words
+    {
+      const unsigned short *qrow = points16 + x * (size_t)D;
+#pragma unroll
+      for (int v = 0; v < KS2; v++) {
+        if (D >= 32) {
+          const uint4 w = *reinterpret_cast<const uint4 *>(qrow + 32 * v + 8 * t4);
+          qw[v][0] = (g8 & 1) ? w.y : w.x;
+          qw[v][1] = (g8 & 1) ? w.w : w.z;
+        } else {                                                  // d = 16: 8 bytes per lane, one k half
+          const uint2 w = *reinterpret_cast<const uint2 *>(qrow + 4 * t4);
+          qw[v][0] = (g8 & 1) ? w.y : w.x;
+          qw[v][1] = 0u;
+        }
+      }
+    }
     const float2 qn = pnrm[x];
     int V = 0;
     {
-      auto load = [&](int b, ScreenRow<D> &r0, ScreenRow<D> &r1, u32 &ce, float2 &ne) {
+      uint4 ra[KS2], rc[KS2];                                    // pieces of candidates g8 and g8+8
+      u32 ce = 0;
+      float2 ne = make_float2(0.f, 0.f);
+      auto load = [&](int b) {
         const u32 c0 = uniq[b + g8], c1 = uniq[b + g8 + 8];
-        r0.load(points16 + (size_t)c0 * D, t4);
-        r1.load(points16 + (size_t)c1 * D, t4);
-        ce = (t4 & 1) ? c1 : c0;                                   // the candidate this lane finishes
+        const unsigned short *p0 = points16 + (size_t)c0 * D, *p1 = points16 + (size_t)c1 * D;
+#pragma unroll
+        for (int v = 0; v < KS2; v++) {
+          if (D >= 32) {
+            ra[v] = *reinterpret_cast<const uint4 *>(p0 + 32 * v + 8 * t4);
+            rc[v] = *reinterpret_cast<const uint4 *>(p1 + 32 * v + 8 * t4);
+          } else {
+            const uint2 w0 = *reinterpret_cast<const uint2 *>(p0 + 4 * t4), w1 = *reinterpret_cast<const uint2 *>(p1 + 4 * t4);
+            ra[v] = make_uint4(w0.x, w0.y, 0u, 0u);
+            rc[v] = make_uint4(w1.x, w1.y, 0u, 0u);
+          }
+        }
+        ce = (t4 & 1) ? c1 : c0;                                  // the candidate this lane finishes
         ne = pnrm[ce];
       };
-      auto eval = [&](int b, const ScreenRow<D> &r0, const ScreenRow<D> &r1, u32 ce, const float2 &ne) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
+      if (U16 > 0) load(0);
+      for (int base = 0; base < U16; base += 16) {
+        float ca[4] = {0.f, 0.f, 0.f, 0.f}, cc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int ks = 0; ks < KS; ks++)
-          mma_f16_16816(c, r0.r[2 * ks], r1.r[2 * ks], r0.r[2 * ks + 1], r1.r[2 * ks + 1], qr16.r[2 * ks], qr16.r[2 * ks + 1]);
-        const float dot = (t4 & 1) ? c[2] : c[0];
-        const float t = qn.x + ne.x;
-        const float lo = __fmaf_rn(-t, t, __fmaf_rn(-2.0f, dot, qn.y + ne.y));
-        const bool pass = t4 < 2 && b + g8 + 8 * (t4 & 1) < U && lo <= tau0s;
+        for (int v = 0; v < KS2; v++) {
+          mma_f16_16816(ca, ra[v].x, ra[v].y, ra[v].z, ra[v].w, qw[v][0], qw[v][1]);
+          mma_f16_16816(cc, rc[v].x, rc[v].y, rc[v].z, rc[v].w, qw[v][0], qw[v][1]);
+        }
+        const u32 cur = ce;
+        const float2 cn = ne;
+        if (base + 16 < U16) load(base + 16);                     // next round's loads fly during the epilogue
+        const float dot = (t4 & 1) ? cc[0] + cc[3] : ca[0] + ca[3];
+        const float t = qn.x + cn.x;
+        const float lo = __fmaf_rn(-t, t, __fmaf_rn(-2.0f, dot, qn.y + cn.y));
+        const bool pass = t4 < 2 && base + g8 + 8 * (t4 & 1) < U && lo <= tau0s;
         const unsigned m = __ballot_sync(FULL, pass);
         if (m) {
-          if (pass) uniq[V + __popc(m & ((1u << lane) - 1))] = ce;
+          if (pass) uniq[V + __popc(m & ((1u << lane) - 1))] = cur;
           V += __popc(m);
-        }
-      };
-      ScreenRow<D> a0, a1, b0, b1;
-      u32 ca = 0, cb = 0;
-      float2 na = make_float2(0.f, 0.f), nb = na;
-      if (U16 > 0) load(0, a0, a1, ca, na);
-      for (int base = 0; base < U16; base += 32) {
-        if (base + 16 < U16) load(base + 16, b0, b1, cb, nb);
-        eval(base, a0, a1, ca, na);
-        if (base + 16 < U16) {
-          if (base + 32 < U16) load(base + 32, a0, a1, ca, na);
-          eval(base + 16, b0, b1, cb, nb);
         }
       }
     }
