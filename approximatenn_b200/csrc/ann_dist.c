@@ -96,6 +96,12 @@ void annb200_dist_shutdown(void) {
   D.rank = 0;
 }
 
+/* gpu_cleanup() pops its hook list, so the next annb200_dist_init() has to register again */
+static void dist_cleanup_hook(void) {
+  annb200_dist_shutdown();
+  D.hooked = 0;
+}
+
 void annb200_dist_init(int rank, int world, const char id_bytes[128]) {
   if (world < 1 || rank < 0 || rank >= world) annh_fatal("%s", "annb200_dist_init: bad rank/world");
   annb200_dist_shutdown();
@@ -108,7 +114,7 @@ void annb200_dist_init(int rank, int world, const char id_bytes[128]) {
   D.rank = rank;
   D.world = world;
   if (!D.hooked) {
-    register_cleanup(annb200_dist_shutdown);
+    register_cleanup(dist_cleanup_hook);
     D.hooked = 1;
   }
 }

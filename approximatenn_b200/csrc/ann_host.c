@@ -454,7 +454,26 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
     free_b += G.arena_bytes;
     while (group > 1 && fixed + group * list_bytes + 512 > free_b * 9 / 10) group--;
   }
+  {
+    /* ANN_B200_MERGE_GROUP=g forces the grouped merge (tests; otherwise only a list set that does
+     * not fit the device triggers it)                                                          */
+    const char *mg = getenv("ANN_B200_MERGE_GROUP");
+    if (!sharded && mg && *mg && atoi(mg) >= 1 && (size_t)atoi(mg) < group) group = (size_t)atoi(mg);
+  }
   if ((size_t)k * T < 16) group = Tl ? Tl : 1;
+  if (!sharded && group < Tl) {
+    /* A running merge sees the lists a group at a time, so rows with EXACT distance ties cannot be
+     * redone with the reference's literal network and the prefix-corner rule is not applied.
+     * Everything else is unchanged.  Say so: the contract elsewhere is bit-exactness.           */
+    static int warned = 0;
+    if (!warned) {
+      fprintf(stderr, "approximatenn_b200: warning: the %zu per-try lists (%.1f GB) do not fit next to the rest of the "
+              "plan; merging %zu at a time. Rows with exact distance ties between different points, and the "
+              "prefix-corner rule (k*tries not a power of two), may differ from the reference in this mode.\n",
+              Tl, Tl * list_bytes / 1e9, group);
+      warned = 1;
+    }
+  }
   annh_arena_reserve(fixed + group * list_bytes + 512);
 
   ftype *dX = annh_arena_take(np * d * w), *dXs = annh_arena_take(n * d * w), *dmean = annh_arena_take(d * w);

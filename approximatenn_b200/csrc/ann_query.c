@@ -115,6 +115,7 @@ static void release_index(void) {
   free(IDX.d_tab);
   free(IDX.cap_tab);
   memset(&IDX, 0, sizeof IDX);
+  cleanup_registered = 0;                          /* gpu_cleanup() ran the hook list: register again next time */
 }
 
 static void reserve_index(size_t n, size_t k, size_t d_short, size_t d, size_t tries) {
@@ -140,6 +141,10 @@ static void reserve_index(size_t n, size_t k, size_t d_short, size_t d, size_t t
 void annh_forget_save(const save_t *save) {
   if (IDX.live && IDX.graph_key == save->graph) drop_index();
 }
+
+/* include/annb200_io.h: callers that rewrite `points` or a save_t IN PLACE (same addresses, same
+ * shape) must say so; the cache key cannot see that (it samples, it does not hash everything).  */
+void annb200_query_cache_invalidate(void) { drop_index(); }
 
 static void upload_narrow(const size_t *host, size_t count, annb_u32 *dst, size_t *tmp, cudaStream_t st) {
   CK(cudaMemcpyAsync(tmp, host, count * sizeof(size_t), cudaMemcpyHostToDevice, st));

@@ -53,6 +53,13 @@ int ann_save_write(const save_t *s, const char *path) {
   return ok ? 0 : -1;
 }
 
+/* ids are point numbers or the sentinel n (pads, alg.c:261-266) */
+static int ids_in_range(const size_t *ids, size_t count, size_t n) {
+  for (size_t i = 0; i < count; i++)
+    if (ids[i] > n) return 0;
+  return 1;
+}
+
 int ann_save_read(save_t *s, const char *path) {
   FILE *f = fopen(path, "rb");
   if (!f) return -1;
@@ -62,6 +69,13 @@ int ann_save_read(save_t *s, const char *path) {
   memset(s, 0, sizeof *s);
   if (fread(magic, 1, 8, f) != 8 || memcmp(magic, MAGIC, 8) || fread(&w, 4, 1, f) != 1 ||
       w != sizeof(ftype) || fread(&tries, 4, 1, f) != 1 || fread(dims, 8, 4, f) != 4) {
+    fclose(f);
+    return -1;
+  }
+  /* the header is not trusted: the limits are the library's own (ann_host.c validate()), the
+   * products below cannot overflow inside them, and every id read later is range-checked      */
+  if (tries < 1 || tries > 64 || dims[0] < 2 || dims[0] >= 0xFFFFFFFFull || dims[1] < 1 || dims[1] > 256 ||
+      dims[1] >= dims[0] || dims[2] > 28 || dims[3] < 1 || dims[3] > ((uint64_t)1 << 20)) {
     fclose(f);
     return -1;
   }
@@ -75,14 +89,15 @@ int ann_save_read(save_t *s, const char *path) {
   int ok = s->par_maxes && s->which_par && s->row_means && s->bases;
   for (uint32_t t = 0; ok && t < tries; t++) {
     uint64_t pm;
-    ok = fread(&pm, 8, 1, f) == 1;
-    s->par_maxes[t] = pm;
+    ok = fread(&pm, 8, 1, f) == 1 && pm <= s->n;                /* a bucket holds at most n points */
+    s->par_maxes[t] = ok ? pm : 0;
   }
   ok = ok && fread(s->row_means, sizeof(ftype), s->d_long, f) == s->d_long;
   ok = ok && fread(s->bases, sizeof(ftype), nb, f) == nb;
-  if (ok) ok = (s->graph = get_ids(f, s->n * s->k)) != NULL;
+  if (ok) ok = (s->graph = get_ids(f, s->n * s->k)) != NULL && ids_in_range(s->graph, s->n * s->k, s->n);
   for (uint32_t t = 0; ok && t < tries; t++)
-    ok = (s->which_par[t] = get_ids(f, s->par_maxes[t] << s->d_short)) != NULL;
+    ok = (s->which_par[t] = get_ids(f, s->par_maxes[t] << s->d_short)) != NULL &&
+         ids_in_range(s->which_par[t], s->par_maxes[t] << s->d_short, s->n);
   fclose(f);
   if (!ok) {
     for (uint32_t t = 0; t < tries && s->which_par; t++) free(s->which_par[t]);

@@ -14,8 +14,16 @@ extern "C" {
 #endif
 /* 0 on success, -1 on I/O error or a file that does not match this build's ftype          */
 int ann_save_write(const save_t *save, const char *path);
-/* fills *save with malloc()ed arrays (release with free_save)                             */
+/* fills *save with malloc()ed arrays (release with free_save); -1 also for a header outside the
+ * library's limits, a truncated file, or ids beyond n                                      */
 int ann_save_read(save_t *save, const char *path);
+
+/* query_gpu keeps the index of the last save_t on the device, keyed on (save->graph, points,
+ * shape) plus a fingerprint of SAMPLED graph / table / point cells — the reference re-ships
+ * everything per call (alg.c:464-508).  A caller that rewrites `points` or the save_t arrays IN
+ * PLACE (same addresses, same shape) must call this (or free_save) before the next query_gpu;
+ * ANN_B200_QUERY_CACHE=0 disables the cache altogether.                                    */
+void annb200_query_cache_invalidate(void);
 #ifdef __cplusplus
 }
 #endif

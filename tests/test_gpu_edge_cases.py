@@ -118,3 +118,25 @@ def test_cleanup_then_reuse(gpu, oracle_mod):
         got.save.free()
         b.lib.gpu_cleanup()
     b.lib.gpu_init()
+
+
+def test_grouped_merge_differs_only_in_tie_rows(oracle_mod, capfd):
+    """ANN_B200_MERGE_GROUP forces the running merge used when the per-try lists do not fit the
+    device.  It cannot redo exact-tie rows literally (and says so on stderr); every other row
+    must still be the reference's, bit for bit.  k*tries is a power of two here, so the
+    prefix-corner rule is not involved."""
+    import os
+    from approximatenn_b200.api import gpu_backend
+    n, d, k, tries = 30000, 64, 16, 8
+    rng = np.random.default_rng(31)
+    pts = rng.standard_normal((n, d)).astype(np.float32)
+    want = oracle_mod.restatement(np.float32).precomp(pts, k, tries, seed=31)
+    os.environ["ANN_B200_MERGE_GROUP"] = "3"
+    try:
+        got = gpu_backend(np.float32).precomp(pts, k, tries, seed=31)
+    finally:
+        del os.environ["ANN_B200_MERGE_GROUP"]
+    bad = np.flatnonzero((got.ids != want.ids).any(axis=1) |
+                         (got.dists.view(np.uint32) != want.dists.view(np.uint32)).any(axis=1))
+    assert len(bad) <= n // 1000, f"{len(bad)} rows differ"
+    assert "merging 3 at a time" in capfd.readouterr().err

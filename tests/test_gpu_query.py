@@ -74,3 +74,52 @@ def test_query_cache_is_dropped_with_the_save(gpu):
         outs.append(q.ids)
         r.save.free()
     assert not np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("n,d,k,tries,ycnt", [(20000, 64, 16, 8, 5000), (9000, 32, 10, 10, 3000), (6000, 16, 32, 3, 1000)])
+def test_pipelined_query_rows_equal_the_generic_kernel(gpu, n, d, k, tries, ycnt):
+    """query_rows_fast_kernel (buffered ids, whole-line loads) vs the warp-per-row kernel it
+    replaces: every bit of ids and distances, with and without self-exclusion."""
+    import os
+    b = gpu[np.dtype(np.float32)]
+    rng = np.random.default_rng(n + d)
+    pts = rng.standard_normal((n, d)).astype(np.float32)
+    y = rng.standard_normal((ycnt, d)).astype(np.float32)
+    r = b.precomp(pts, k, tries, want_save=True, seed=9)
+    fast, fast_s = b.query(r.save, pts, y), b.query(r.save, pts, pts)
+    os.environ["ANN_B200_NO_FAST_QUERY"] = "1"
+    try:
+        slow, slow_s = b.query(r.save, pts, y), b.query(r.save, pts, pts)
+    finally:
+        del os.environ["ANN_B200_NO_FAST_QUERY"]
+    for a, c in ((fast, slow), (fast_s, slow_s)):
+        assert np.array_equal(a.ids, c.ids) and same_bits(a.dists, c.dists)
+    r.save.free()
+
+
+def test_corrected_sign_layout_is_opt_in_and_finds_the_point_itself(gpu):
+    """ANN_B200_QUERY_LAYOUT=fixed reads the sign buffer the way it was written ([x][try]).
+    Querying copies of indexed points then lands in the point's own bucket in every try, so the
+    nearest neighbour is the point itself at distance 0; the reference's transposed read
+    (the default, reproduced bit for bit elsewhere in this file) sends most queries to unrelated
+    buckets."""
+    import os
+    b = gpu[np.dtype(np.float32)]
+    rng = np.random.default_rng(77)
+    n, d, k, tries = 16384, 16, 10, 10
+    pts = rng.standard_normal((n, d)).astype(np.float32)
+    rows = rng.choice(n, size=2000, replace=False)
+    y = pts[rows].copy()                                   # not the same pointer: no self-exclusion
+    r = b.precomp(pts, k, tries, want_save=True, seed=13)
+    default = b.query(r.save, pts, y)
+    os.environ["ANN_B200_QUERY_LAYOUT"] = "fixed"
+    try:
+        fixed = b.query(r.save, pts, y)
+    finally:
+        del os.environ["ANN_B200_QUERY_LAYOUT"]
+    hit_fixed = float(np.mean((fixed.ids[:, 0] == rows) & (fixed.dists[:, 0] == 0)))
+    hit_default = float(np.mean(default.ids[:, 0] == rows))
+    print(f"own point found first: fixed layout {hit_fixed:.3f}, reference layout {hit_default:.3f}")
+    assert hit_fixed > 0.999
+    assert hit_default < 0.9
+    r.save.free()
