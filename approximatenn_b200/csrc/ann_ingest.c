@@ -58,6 +58,8 @@ static int ingest_threads(void) {
   const char *env = getenv("ANN_B200_INGEST_THREADS");
   if (env && *env) nt = atoi(env);
   long cores = sysconf(_SC_NPROCESSORS_ONLN);
+  int world = annh_dist_world();                  /* one process per GPU shares the box's cores */
+  if (world > 1 && !(env && *env)) { int share = (int)(cores / world) - 2; if (nt > share) nt = share < 2 ? 2 : share; }
   if (cores > 2 && nt > cores - 2) nt = (int)cores - 2;
   if (nt < 1) nt = 1;
   if (nt > INGEST_MAX_THREADS) nt = INGEST_MAX_THREADS;

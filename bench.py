@@ -12,7 +12,8 @@ Printed JSON (one line, rank 0):
             (CUDA events on the library's stream, from after the upload to before the download)
   e2e       points/s through the reference-facing C-ABI call precomp_gpu(host pointers), the
             time_results protocol (time_results.c:90-129): malloc()ed (pageable) host input ->
-            H2D -> all stages -> D2H into the malloc()ed result arrays, free() of the results.
+            H2D -> all stages -> D2H into the malloc()ed result arrays; the clock brackets the
+            call, free() of the results happens outside it as in time_results.
             e2e.pinned repeats it with a page-locked input buffer.
   roofline  the dominant kernel against measured peaks (MEASURED_PEAKS.json for HBM, the
             library's own FFMA probe for the FP32 pipe)
@@ -402,10 +403,14 @@ def main():
     pts_pinned = host.numpy()
     pts_pinned[:] = pts
 
+    call_s = [0.0]                     # time inside precomp_gpu, summed (time_results.c:121-129)
+
     def step(src=pts, keep=None):
         dptr = ctypes.c_void_p()
         srandom(SEED)
+        t_in = time.perf_counter()
         ids = gpu.precomp_raw(n, k, d, src.ctypes.data, tries, *ROT, None, ctypes.byref(dptr))
+        call_s[0] += time.perf_counter() - t_in
         st = stage_times(gpu)
         if keep is not None:
             keep(ids, dptr)
@@ -445,18 +450,20 @@ def main():
     step()
     barrier()
     t0 = time.perf_counter()
+    call_s[0] = 0.0
     for _ in range(args.steps):
         step()
     barrier()
-    wall = time.perf_counter() - t0
+    wall_loop = time.perf_counter() - t0
+    wall = call_s[0]
     # timed region 3: page-locked caller buffer (extra)
     step(pts_pinned)
     barrier()
-    t0 = time.perf_counter()
+    call_s[0] = 0.0
     for _ in range(args.steps):
         step(pts_pinned)
     barrier()
-    wall_pinned = time.perf_counter() - t0
+    wall_pinned = call_s[0]
     gpu.lib.annh_set_timing(1)
     sampler.stop_flag.set()
     sampler.join()
@@ -483,9 +490,9 @@ def main():
     dev_total_s = sum(dev_ms) / 1e3
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([dev_total_s, wall, wall_pinned], device="cuda", dtype=torch.float64)
+        t = torch.tensor([dev_total_s, wall, wall_pinned, wall_loop], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_total_s, wall, wall_pinned = float(t[0]), float(t[1]), float(t[2])
+        dev_total_s, wall, wall_pinned, wall_loop = float(t[0]), float(t[1]), float(t[2]), float(t[3])
         parts = [None] * world if rank == 0 else None
         dist.gather_object((mine, kept["ids"], kept["d"]), parts, dst=0)
         stage_all = [None] * world if rank == 0 else None
@@ -569,7 +576,11 @@ def main():
             "e2e": {"value": n * args.steps / wall, "unit": "points/s",
                     "h2d_bytes_per_step": n * d * w, "d2h_bytes_per_step": n * k * (4 + w),
                     "ms_per_step": 1e3 * wall / args.steps,
-                    "input": "malloc()ed (pageable) host array, the time_results protocol",
+                    "input": "malloc()ed (pageable) host array",
+                    "timed": "time inside the K precomp_gpu calls (host pointers in, malloc()ed arrays out), the "
+                             "clock placement of the reference's time_results (time_results.c:121-129): free() of "
+                             "the results is outside; max over ranks",
+                    "ms_per_step_loop_with_free": 1e3 * wall_loop / args.steps,
                     "ms_per_step_with_stage_events": 1e3 * wall_instrumented / args.steps,
                     "pinned": {"value": n * args.steps / wall_pinned, "ms_per_step": 1e3 * wall_pinned / args.steps,
                                "input": "page-locked host array"}},
