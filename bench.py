@@ -328,6 +328,69 @@ def run_reference_arm(args, cfg, name):
     print(json.dumps(line), flush=True)
 
 
+def extra_config_run(gpu, name, world, rank, steps=3, warmup=1):
+    """A second, shorter measurement on another BASELINE config inside the same job (the N=8 line
+    carries config 4, n = 10^7, this way while the scaling series itself stays on config 3).
+    Device time from the stage events, call time as in `e2e`; instead of the oracle (its
+    single-threaded table build alone takes minutes at this size) sampled rows are checked for the
+    properties every correct result has: ascending distances, valid ids, no self, and squared
+    distances equal to a float64 recomputation within 1e-5 relative (north_star's tolerance)."""
+    import torch
+    from approximatenn_b200.api import srandom, stage_times, _libc, _view
+    n, d, k, tries, dtype = CONFIGS[name]
+    pts = synth_points(n, d, dtype)
+    lo, hi = 0, n
+    if world > 1:
+        from approximatenn_b200 import dist as adist
+        lo, hi = adist.row_slice(gpu.lib, n, rank, world)
+    dev, call, kept = [], [], {}
+
+    def one(i):
+        dptr = ctypes.c_void_p()
+        srandom(SEED)
+        t0 = time.perf_counter()
+        ids = gpu.precomp_raw(n, k, d, pts.ctypes.data, tries, *ROT, None, ctypes.byref(dptr))
+        dt = time.perf_counter() - t0
+        st = stage_times(gpu)
+        if i == warmup + steps - 1 and hi > lo:
+            rows = np.sort(np.random.default_rng(3 + rank).choice(hi - lo, size=min(64, hi - lo), replace=False))
+            kept["rows"] = rows + lo
+            kept["ids"] = _view(ids, (hi - lo, k), np.uint64)[rows].copy()
+            kept["d"] = _view(dptr, (hi - lo, k), dtype)[rows].copy()
+        _libc.free(ids); _libc.free(dptr)
+        return dt, st
+
+    for i in range(warmup + steps):
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        dt, st = one(i)
+        if i >= warmup:
+            call.append(dt)
+            dev.append(sum(st[k_] for k_ in ("means", "hash", "buckets", "leaf", "exchange", "merge", "supercharge")))
+            last = st
+    bad = 0
+    if kept:
+        ids_, d_ = kept["ids"].astype(np.int64), kept["d"].astype(np.float64)
+        exact = ((pts[kept["rows"]][:, None, :].astype(np.float64) - pts[np.minimum(ids_, n - 1)].astype(np.float64)) ** 2).sum(-1)
+        ok = (ids_ < n).all(axis=1) & (ids_ != kept["rows"][:, None]).all(axis=1) & (np.diff(d_, axis=1) >= 0).all(axis=1) & \
+            (np.abs(exact - d_) <= 1e-5 * np.maximum(exact, 1e-30)).all(axis=1)
+        bad = int((~ok).sum())
+    t = torch.tensor([sum(dev) / 1e3, sum(call), float(bad), float(len(kept.get("rows", ())))], device="cuda", dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        t = torch.stack([mx[0], mx[1], sm[2], sm[3]])
+    return {"config": workload_config(CONFIGS[name], name, world), "steps": steps, "warmup": warmup,
+            "value": n * steps / float(t[0]), "unit": "points/s", "ms_per_step": 1e3 * float(t[0]) / steps,
+            "e2e": {"value": n * steps / float(t[1]), "ms_per_step": 1e3 * float(t[1]) / steps},
+            "stage_ms_rank0_last_step": last,
+            "sanity_rows": {"rows": int(t[3]), "failing": int(t[2]),
+                            "checked": "ascending distances, ids < n and != the point, squared distances vs a "
+                                       "float64 recomputation within 1e-5 relative"}}
+
+
 def workload_config(cfg, name, gpus):
     n, d, k, tries, dtype = cfg
     return {"workload": f"BASELINE {name}: n={n} d={d} k={k} {np.dtype(dtype).name}, {tries} tries + supercharge, "
@@ -356,6 +419,8 @@ def main():
                     help="--impl reference: also time BASELINE config 1 directly (adds ~20-45 s)")
     ap.add_argument("--pair-queries", type=int, default=65536,
                     help="query vectors of the precomp(save)+query pair measurement (0 = skip)")
+    ap.add_argument("--extra-config", default="auto", choices=["auto", "none", "cfg4", "cfg5"],
+                    help="second, shorter measurement in the same job (auto: cfg4 at 8 GPUs on cfg3)")
     ap.add_argument("--recall-sample", type=int, default=2000,
                     help="points whose exact k nearest neighbours are brute-forced for recall@k (0 = skip)")
     args = ap.parse_args()
@@ -510,6 +575,10 @@ def main():
         st_ = gpu.lib.annh_stream()
         fp32_probe = {m_: float(gpu.lib.annb_probe_fp32(i_, 3, st_)) for i_, m_ in
                       enumerate(("ffma", "fmul_fadd", "ffma2", "fmul2_fadd2"))}
+    extra_name = args.extra_config
+    if extra_name == "auto":
+        extra_name = "cfg4" if (world == 8 and args.config == "cfg3") else "none"
+    extra = extra_config_run(gpu, extra_name, world, rank) if extra_name != "none" else None
     if world > 1:
         gpu.lib.annb200_dist_shutdown()
         dist.barrier()
@@ -588,6 +657,8 @@ def main():
             "roofline_step": roofline_step, "clocks": sampler.summary(), "host_cores": os.cpu_count()}
     if world > 1:
         line["stage_ms_per_rank"] = stage_all
+    if extra is not None:
+        line[extra_name] = extra
     if args.recall_sample > 0 and world == 1:
         line["recall"] = measure_recall(gpu, pts, cfg, args.recall_sample)
     if args.pair_queries > 0 and world == 1:
