@@ -419,7 +419,7 @@ def main():
                     help="--impl reference: also time BASELINE config 1 directly (adds ~20-45 s)")
     ap.add_argument("--pair-queries", type=int, default=65536,
                     help="query vectors of the precomp(save)+query pair measurement (0 = skip)")
-    ap.add_argument("--extra-config", default="auto", choices=["auto", "none", "cfg4", "cfg5"],
+    ap.add_argument("--extra-config", default="auto", choices=["auto", "none"] + sorted(CONFIGS),
                     help="second, shorter measurement in the same job (auto: cfg4 at 8 GPUs on cfg3)")
     ap.add_argument("--recall-sample", type=int, default=2000,
                     help="points whose exact k nearest neighbours are brute-forced for recall@k (0 = skip)")
