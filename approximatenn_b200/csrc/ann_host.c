@@ -438,6 +438,17 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
                  pad256(scratch_bytes) + 8192 + 256;
   const int s5_screened = annb_supercharge_screen_applies(d, k);
   if (s5_screened) fixed += pad256(n * d * 2) + pad256(n * 8); /* fp16 copy of the points (original order) + norms */
+  /* ANN_B200_S5_LOCALITY=1: rows worked on in bucket order of one try.  Off by default: on iid
+   * Gaussian points (the benchmark data) it changes neither the L2 hit rate nor the time (cfg3
+   * 4.96 vs 4.92 ms, cfg4 112 vs 112 ms) — the candidates of a row come from the
+   * other tries' buckets and share nothing with its bucket neighbours'.                         */
+  int s5_local = 0;
+  {
+    const char *e = getenv("ANN_B200_S5_LOCALITY");
+    if (e && *e && *e != '0') s5_local = s5_screened && Tl > 0;
+  }
+  const size_t local_bytes = s5_local ? annb_locality_scratch_bytes(my_rows, d_short, 8) : 0;
+  if (s5_local) fixed += pad256(local_bytes) + pad256(my_rows * 4);
   if (sharded && save) fixed += pad256(T * n * 4);            /* every try's hashes, for the tables */
   if (sharded)   /* merged ids (all rows), merged dists + results (own rows), exchanged lists */
     fixed += pad256(np * k * 4) + pad256(my_rows * k * w) + pad256(my_rows * k * 4) + pad256(my_rows * k * w) +
@@ -504,6 +515,8 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   const int screened = annb_screen_applies(d, d_short, k);
   void *dX16 = s5_screened ? annh_arena_take(n * d * 2) : NULL;
   void *dN16 = s5_screened ? annh_arena_take(n * 8) : NULL;
+  void *dlocal = s5_local ? annh_arena_take(local_bytes) : NULL;
+  annb_u32 *dperm = s5_local ? annh_arena_take(my_rows * 4) : NULL;
   annb_u32 *dhash_all = (sharded && save) ? annh_arena_take(T * n * 4) : NULL;
   annb_u32 *ds_ids = sharded ? annh_arena_take(T * my_rows * k * 4) : NULL;   /* [T][my_rows][k] */
   ftype *ds_dist = sharded ? annh_arena_take(T * my_rows * k * w) : NULL;
@@ -646,8 +659,17 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   /* 7. S5 supercharging of the owned rows (alg.c:313-327); graph = the merged lists        */
   {
     annb_supercharge_opts s5;
-    s5.points16 = dX16; s5.nrm = dN16; s5.scale_bits = dscreen; s5.row_perm = NULL;
+    s5.points16 = dX16; s5.nrm = dN16; s5.scale_bits = dscreen; s5.row_perm = NULL; s5.perm_base = row_lo;
     int nch = full_result && sharded ? 1 : annh_egress_chunks(eg);
+    if (s5_local && my_rows) {
+      size_t lo[65];
+      for (int c = 0; c < nch; c++) lo[c] = (my_rows * (size_t)c / nch) & ~(size_t)31;
+      lo[nch] = my_rows;
+      sp = span_begin(7);
+      annb_locality_order(dhash + (Tl - 1) * n, row_lo, my_rows, d_short, nch, lo, dlocal, dperm, st);
+      span_end(sp);
+      s5.row_perm = dperm;
+    }
     for (int c = 0; c < nch; c++) {
       size_t r0 = row_lo + ((my_rows * (size_t)c / nch) & ~(size_t)31);
       size_t r1 = c + 1 == nch ? row_hi : row_lo + ((my_rows * (size_t)(c + 1) / nch) & ~(size_t)31);

@@ -842,7 +842,7 @@ extern "C" void annb_supercharge(const FT *queries, const FT *points, const u32 
     dim3 block(256), grid(grid_for(rows * 32, 256));
     const unsigned short *p16 = (const unsigned short *)opts->points16;
     const float2 *pn = (const float2 *)opts->nrm;
-#define SCREEN_CASE(DD) supercharge_screen_kernel<DD><<<grid, block, ssmem, stream>>>(points, p16, pn, opts->scale_bits, own_ids, own_dist, graph, n, (int)k, row_begin, row_end, row_perm, out_ids, out_dist, ls.list)
+#define SCREEN_CASE(DD) supercharge_screen_kernel<DD><<<grid, block, ssmem, stream>>>(points, p16, pn, opts->scale_bits, own_ids, own_dist, graph, n, (int)k, row_begin, row_end, row_perm, opts->perm_base, out_ids, out_dist, ls.list)
     switch (d) {
       case 16: SCREEN_CASE(16); break;
       case 32: SCREEN_CASE(32); break;

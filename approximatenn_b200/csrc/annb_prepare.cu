@@ -642,9 +642,70 @@ __global__ void sort_buckets_kernel(const u32 *__restrict__ order_tmp,
   }
 }
 
+extern "C" size_t annb_scan_tmp_bytes(size_t buckets);
+
+// ---- S5 locality order ---------------------------------------------------------------------
+// Rows of one supercharge chunk are worked on in the order of their leading hash bits of one
+// try: neighbouring warps then gather overlapping candidate rows (points that share a bucket
+// prefix share most of their neighbours' neighbours), which turns DRAM gathers into L2 hits.
+// key = chunk * 2^bits + (hash >> shift); rows are grouped by key with the S2 machinery
+// (histogram, scan, scatter); the order inside a key does not matter.
+struct ChunkBounds { unsigned n; unsigned lo[65]; };          // chunk c = relative rows [lo[c], lo[c+1])
+
+__global__ void locality_keys_kernel(const u32 *__restrict__ hash, size_t row_lo, size_t rows, int shift, int bits,
+                                     ChunkBounds cb, u32 *__restrict__ keys) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  unsigned c = 0;
+  while (c + 1 < cb.n && (unsigned)i >= cb.lo[c + 1]) c++;
+  keys[i] = (c << bits) | (hash[row_lo + i] >> shift);
+}
+
+static int locality_bits(size_t d_short) { return d_short < 17 ? (int)d_short : 17; }
+
+extern "C" size_t annb_locality_scratch_bytes(size_t rows, size_t d_short, int chunks) {
+  size_t nkeys = (size_t)chunks << locality_bits(d_short);
+  return ((rows * 4 + 255) & ~(size_t)255) + ((nkeys * 4 + 255) & ~(size_t)255) + (((nkeys + 1) * 4 + 255) & ~(size_t)255) +
+         ((annb_scan_tmp_bytes(nkeys) + 255) & ~(size_t)255) + 256;
+}
+
+extern "C" void annb_locality_order(const u32 *hash, size_t row_lo, size_t rows, size_t d_short, int chunks,
+                                    const size_t *chunk_lo, void *scratch, u32 *perm, annb_stream stream) {
+  if (rows == 0) return;
+  if (chunks < 1 || chunks > 64) fatal_config("annb_locality_order: 1..64 chunks");
+  const int bits = locality_bits(d_short), shift = (int)d_short - bits;
+  const size_t nkeys = (size_t)chunks << bits;
+  unsigned char *p = (unsigned char *)scratch;
+  u32 *keys = (u32 *)p;
+  p += (rows * 4 + 255) & ~(size_t)255;
+  u32 *count = (u32 *)p;
+  p += (nkeys * 4 + 255) & ~(size_t)255;
+  u32 *offset = (u32 *)p;
+  p += ((nkeys + 1) * 4 + 255) & ~(size_t)255;
+  u32 *block_tot = (u32 *)p;
+  ChunkBounds cb;
+  cb.n = (unsigned)chunks;
+  for (int c = 0; c <= chunks; c++) cb.lo[c] = (unsigned)chunk_lo[c];
+  const size_t blocks = (nkeys + SCAN_ITEMS - 1) / SCAN_ITEMS;
+  RT_CHECK(cudaMemsetAsync(count, 0, nkeys * sizeof(u32), stream));
+  RT_CHECK(cudaMemsetAsync(block_tot + blocks, 0, sizeof(u32), stream));        // the unused "tmax" word
+  locality_keys_kernel<<<grid_for(rows, 256), 256, 0, stream>>>(hash, row_lo, rows, shift, bits, cb, keys);
+  LAUNCH_CHECK("locality_keys");
+  histogram_kernel<<<grid_for(rows, 256), 256, 0, stream>>>(keys, rows, count);
+  LAUNCH_CHECK("histogram");
+  scan_blocks_kernel<<<(unsigned)blocks, SCAN_THREADS, 0, stream>>>(count, nkeys, offset, block_tot, block_tot + blocks);
+  LAUNCH_CHECK("scan_blocks");
+  scan_totals_kernel<<<1, 1024, 0, stream>>>(block_tot, blocks);
+  LAUNCH_CHECK("scan_totals");
+  scan_addback_kernel<<<(unsigned)blocks, SCAN_THREADS, 0, stream>>>(offset, nkeys, block_tot, (u32)rows);
+  LAUNCH_CHECK("scan_addback");
+  scatter_kernel<<<grid_for(rows, 256), 256, 0, stream>>>(keys, rows, offset, count, perm);
+  LAUNCH_CHECK("scatter");
+}
+
 extern "C" size_t annb_scan_tmp_bytes(size_t buckets) {
   size_t blocks = (buckets + SCAN_ITEMS - 1) / SCAN_ITEMS;
-  return (blocks + 1) * sizeof(u32);
+  return (blocks + 2) * sizeof(u32);
 }
 
 extern "C" void annb_build_buckets(const u32 *hash, size_t n, size_t buckets, u32 *count,

@@ -37,7 +37,7 @@ supercharge_screen_kernel(const float *__restrict__ points, const unsigned short
                           const float2 *__restrict__ pnrm, const unsigned *__restrict__ scale_bits,
                           const u32 *__restrict__ own_ids,
                           const float *__restrict__ own_dist, const u32 *__restrict__ graph, size_t n,
-                          int k, size_t row_begin, size_t row_end, const u32 *__restrict__ row_perm,
+                          int k, size_t row_begin, size_t row_end, const u32 *__restrict__ row_perm, size_t perm_base,
                           u32 *__restrict__ out_ids, float *__restrict__ out_dist, TieList ties) {
   constexpr int LPC = D / 8;                         // exact tree: lanes per candidate, 32 bytes of fp32 each
   constexpr int CPR = 32 / LPC;                      // exact tree: candidates per round
@@ -49,7 +49,7 @@ supercharge_screen_kernel(const float *__restrict__ points, const unsigned short
   __syncthreads();
   const size_t pos = row_begin + (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (pos < row_end) {
-    const size_t x = row_perm ? (size_t)row_perm[pos] : pos;
+    const size_t x = row_perm ? perm_base + (size_t)row_perm[pos - perm_base] : pos;
     const u32 sentinel = (u32)n;
     const float inf = ft_inf();
     const int wide = k * (k + 1);

@@ -165,19 +165,29 @@ void annb_merge_lists(const annb_u32 *lists_ids, const ftype *lists_dist, int n_
  *                        candidates are bracketed from them and only those that can reach the
  *                        row's k best are measured exactly (float, d in {16,32,64,128}, k <= 32;
  *                        same rows bit for bit; ANN_B200_S5_SCREEN=0 switches it off)
- *   row_perm             a permutation of [row_begin, row_end) (indexed by row): the order in
- *                        which the rows are worked on (locality), NULL = ascending                */
+ *   row_perm/perm_base   the order in which the rows are worked on (annb_locality_order):
+ *                        positions [row_begin, row_end) must map onto exactly those rows;
+ *                        NULL = ascending                                                        */
 typedef struct {
   const void *points16;
   const void *nrm;
   const unsigned *scale_bits;
-  const annb_u32 *row_perm;
+  const annb_u32 *row_perm;   /* row worked on at position p of the call: perm_base + row_perm[p - perm_base] */
+  size_t perm_base;
 } annb_supercharge_opts;
 void annb_supercharge(const ftype *queries, const ftype *points, const annb_u32 *own_ids,
                       const ftype *own_dist, const annb_u32 *graph, size_t n, size_t d,
                       size_t k, size_t row_begin, size_t row_end, int exclude_self,
                       annb_u32 *out_ids, ftype *out_dist, void *scratch, size_t scratch_bytes,
                       int *status, const annb_supercharge_opts *opts, annb_stream stream);
+/* Locality order for the supercharge (the lever SURVEY 8.D names for its gather term): relative
+ * rows [0, rows) of the slice starting at row_lo, grouped by chunk (chunk c = relative rows
+ * [chunk_lo[c], chunk_lo[c+1]), host array of chunks+1 entries) and inside a chunk by the leading
+ * bits of `hash` (one try's bucket ids, indexed by global row).  perm: rows entries.             */
+size_t annb_locality_scratch_bytes(size_t rows, size_t d_short, int chunks);
+void annb_locality_order(const annb_u32 *hash, size_t row_lo, size_t rows, size_t d_short, int chunks,
+                         const size_t *chunk_lo, void *scratch, annb_u32 *perm, annb_stream stream);
+
 /* 1 (default) / 0: the screened supercharge and the thread-per-point merge can be switched off at
  * run time (ANN_B200_S5_SCREEN=0, ANN_B200_THREAD_MERGE=0 do the same); results are identical  */
 void annb_supercharge_screen_mode(int on);

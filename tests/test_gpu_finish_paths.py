@@ -79,3 +79,22 @@ def test_fast_paths_equal_oracle(oracle_mod, dtype, n, d, k, tries):
     got = gpu.precomp(pts, k, tries, seed=17)
     assert np.array_equal(got.ids, want.ids)
     assert same_bits(got.dists, want.dists)
+
+
+@pytest.mark.parametrize("n,d,k,tries", [(140000, 64, 16, 4), (20000, 32, 10, 5), (3000, 16, 5, 6)])
+def test_locality_order_does_not_change_a_bit(gpu32, n, d, k, tries):
+    """With ANN_B200_S5_LOCALITY=1 the supercharge works on its rows in bucket order of one try
+    (annb_locality_order); the rows it writes must not depend on that order.  n = 140000 has 8 egress chunks, each with its
+    own permutation."""
+    import os
+    rng = np.random.default_rng(n)
+    pts = rng.standard_normal((n, d)).astype(np.float32)
+    gpu32.lib.annb_supercharge_screen_mode(1)
+    off = gpu32.precomp(pts, k, tries, seed=5)
+    os.environ["ANN_B200_S5_LOCALITY"] = "1"
+    try:
+        on = gpu32.precomp(pts, k, tries, seed=5)
+    finally:
+        del os.environ["ANN_B200_S5_LOCALITY"]
+    assert np.array_equal(on.ids, off.ids)
+    assert same_bits(on.dists, off.dists)
