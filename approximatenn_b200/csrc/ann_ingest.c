@@ -99,7 +99,7 @@ void annh_ingest(void *dst, const void *src, size_t bytes, void *consumer, int d
   const char *env = getenv("ANN_B200_STAGED_UPLOAD");
   if (env && *env == '0') pageable = 0;
   long cores = sysconf(_SC_NPROCESSORS_ONLN);
-  if (!pageable || bytes < ((size_t)32 << 20) || cores < 4) {
+  if (!pageable || bytes < ((size_t)8 << 20) || cores < 4) {
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
     return;
   }
@@ -113,7 +113,11 @@ void annh_ingest(void *dst, const void *src, size_t bytes, void *consumer, int d
       CK(cudaEventCreateWithFlags(&I.slot_free[i], cudaEventDisableTiming | cudaEventBlockingSync));
     I.ready = 1;
   }
-  const int nt = ingest_threads();
+  int nt = ingest_threads();
+  {                                                  /* a thread per 4 MB chunk at most */
+    size_t chunks = (bytes + INGEST_CHUNK - 1) / INGEST_CHUNK;
+    if ((size_t)nt > chunks) nt = (int)chunks;
+  }
   pthread_t th[INGEST_MAX_THREADS];
   ingest_job job[INGEST_MAX_THREADS];
   for (int i = 0; i < nt; i++) {

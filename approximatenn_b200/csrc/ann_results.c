@@ -155,6 +155,10 @@ annh_egress *annh_egress_begin(size_t rows, size_t k, int want_dist, int want_se
   int nt = cores >= 12 ? 6 : 4;
   const char *env = getenv("ANN_B200_HOST_THREADS");
   if (env && *env) nt = atoi(env);
+  else if (annh_dist_world() > 1) {               /* one process per GPU shares the box's cores */
+    int share = (int)(cores / annh_dist_world()) - 1;
+    if (nt > share) nt = share < 1 ? 1 : share;
+  }
   if (cores > 1 && nt > cores - 1) nt = (int)cores - 1;
   if (rows * k < ((size_t)1 << 18)) nt = 1;
   if (nt < 1) nt = 1;

@@ -1,4 +1,4 @@
-"""The staged upload of pageable caller memory (csrc/ann_ingest.c: >= 32 MB goes through a ring
+"""The staged upload of pageable caller memory (csrc/ann_ingest.c: >= 8 MB goes through a ring
 of pinned slots filled by host threads).  The same points are handed over three ways — plain
 malloc()ed memory (staged path), page-locked memory, and pageable memory with the staging
 switched off (one cudaMemcpyAsync) — and must give identical results; sampled rows are checked
