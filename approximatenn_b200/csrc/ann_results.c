@@ -76,6 +76,17 @@ void annh_egress_release(void) {
   }
 }
 
+/* Makes the pages of [p, p+bytes) of a fresh malloc() resident by touching them.  (Asking the
+ * kernel to populate the range instead — madvise(MADV_POPULATE_WRITE), with or without huge
+ * pages — was measured 15-25 ms SLOWER per call at cfg3 on the GPU boxes: the call holds the
+ * address-space lock the CUDA driver and the other threads need.)                             */
+static void make_resident(void *p, size_t bytes) {
+  if (!bytes) return;
+  volatile char *c = (volatile char *)p;
+  for (size_t o = 0; o < bytes; o += 4096) c[o] = 0;
+  c[bytes - 1] = 0;
+}
+
 static void *egress_worker(void *p) {
   struct annh_egress *e = ((egress_arg *)p)->e;
   const int me = ((egress_arg *)p)->idx;
@@ -85,19 +96,9 @@ static void *egress_worker(void *p) {
    *    cell written in step 2 (a chunk may land while a slow thread is still touching).     */
   {
     size_t lo = (e->rows * (size_t)me / e->nthreads) * e->k, hi = (e->rows * (size_t)(me + 1) / e->nthreads) * e->k;
-    volatile char *a = (volatile char *)(e->ids + lo);
-    for (size_t o = 0; o < (hi - lo) * sizeof(size_t); o += 4096) a[o] = 0;
-    if (hi > lo) a[(hi - lo) * sizeof(size_t) - 1] = 0;
-    if (e->ids2) {
-      volatile char *a2 = (volatile char *)(e->ids2 + lo);
-      for (size_t o = 0; o < (hi - lo) * sizeof(size_t); o += 4096) a2[o] = 0;
-      if (hi > lo) a2[(hi - lo) * sizeof(size_t) - 1] = 0;
-    }
-    if (e->dist) {
-      volatile char *b = (volatile char *)(e->dist + lo);
-      for (size_t o = 0; o < (hi - lo) * sizeof(ftype); o += 4096) b[o] = 0;
-      if (hi > lo) b[(hi - lo) * sizeof(ftype) - 1] = 0;
-    }
+    make_resident(e->ids + lo, (hi - lo) * sizeof(size_t));
+    if (e->ids2) make_resident(e->ids2 + lo, (hi - lo) * sizeof(size_t));
+    if (e->dist) make_resident(e->dist + lo, (hi - lo) * sizeof(ftype));
   }
   pthread_barrier_wait(&e->touched);
   /* 2. every chunk, as it lands: this thread widens/copies its 1/nthreads share of the rows,
@@ -175,7 +176,10 @@ annh_egress *annh_egress_begin(size_t rows, size_t k, int want_dist, int want_se
 }
 
 int annh_egress_chunks(const annh_egress *e) {
-  return e->rows >= ((size_t)1 << 17) ? 8 : 1;
+  /* chunks of at least 16k rows, so that the copy and the widening of a chunk hide behind the
+   * computation of the next ones also when a rank owns a small slice                        */
+  size_t c = e->rows >> 14;
+  return c >= 8 ? 8 : c >= 2 ? (int)c : 1;
 }
 
 void annh_egress_chunk(annh_egress *e, size_t r0, size_t r1, const void *dev_ids,
