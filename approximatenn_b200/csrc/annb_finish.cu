@@ -218,107 +218,99 @@ merge_lists_thread_kernel(const u32 *__restrict__ lists_ids, const FT *__restric
   const size_t x0 = (size_t)blockIdx.x * PT;
   const int pts = (int)min((size_t)PT, n - x0);
   const int NS = a.n_src;
-  // row layout (words): dist [NS][k] (FW words each) | out dist [k] | ids [NS][k] | out ids [k]
-  const int off_od = NS * k * FW, off_ids = off_od + k * FW, off_oi = off_ids + NS * k;
-  // ---- stage: for every list, the pts*k entries of this CTA are contiguous in global memory
+  // Only the DISTANCES are staged (row of a point: [NS][k] distances, then k 16-bit codes of
+  // the emitted entries): the order of the merge is decided by them alone.  An id is needed
+  // (a) for the k entries that are kept — fetched after the walk, k independent loads — and
+  // (b) when a head has exactly the distance emitted last: the same id again (a duplicate,
+  // equal ids carry equal distances) or a different one (an exact tie -> literal kernel).
+  // Half the shared memory per point doubles the resident warps of this latency-bound kernel.
+  const int off_code = NS * k * FW;
   for (int s = 0; s < NS; s++) {
     const size_t g0 = ((size_t)a.src[s] * n + x0) * k;
     const int cells = pts * k;
     if ((k & 3) == 0 && FW == 1) {
-      const uint4 *gi = reinterpret_cast<const uint4 *>(lists_ids + g0);
       const uint4 *gd = reinterpret_cast<const uint4 *>(lists_dist + g0);
       for (int e = tid; e < cells / 4; e += PT) {
         const int p = (4 * e) / k, z = 4 * e - p * k;
-        *reinterpret_cast<uint4 *>(sm + (size_t)p * row_words + off_ids + s * k + z) = gi[e];
-        *reinterpret_cast<uint4 *>(sm + (size_t)p * row_words + (s * k + z) * FW) = gd[e];
+        *reinterpret_cast<uint4 *>(sm + (size_t)p * row_words + s * k + z) = gd[e];
       }
     } else {
       for (int e = tid; e < cells; e += PT) {
         const int p = e / k, z = e - p * k;
-        sm[(size_t)p * row_words + off_ids + s * k + z] = lists_ids[g0 + e];
         *reinterpret_cast<FT *>(sm + (size_t)p * row_words + (s * k + z) * FW) = lists_dist[g0 + e];
       }
     }
   }
   __syncthreads();
-  if (tid < pts) {
-    u32 *row = sm + (size_t)tid * row_words;
-    const FT *rd = reinterpret_cast<const FT *>(row);
-    const u32 *ri = row + off_ids;
-    FT *od = reinterpret_cast<FT *>(row + off_od);
-    u32 *oi = row + off_oi;
-    const FT inf = ft_inf();
-    FT hv[ML];
-    u32 hid[ML];
-    int hp[ML];
+  if (tid >= pts) return;
+  const size_t x = x0 + tid;
+  u32 *row = sm + (size_t)tid * row_words;
+  const FT *rd = reinterpret_cast<const FT *>(row);
+  unsigned short *code = reinterpret_cast<unsigned short *>(row + off_code);
+  auto id_of = [&](int slot, int pos) { return lists_ids[((size_t)a.src[slot] * n + x) * k + pos]; };
+  const FT inf = ft_inf();
+  FT hv[ML];
+  int hp[ML];
 #pragma unroll
-    for (int s = 0; s < ML; s++) {
-      const bool on = s < NS && a.admit[s] > 0;
-      hv[s] = on ? rd[s * k] : inf;
-      hid[s] = on ? ri[s * k] : sentinel;
-      hp[s] = 0;
-    }
-    int out = 0;
-    u32 last_id = sentinel;
-    FT last_v = -inf;
-    bool tie = false;
-    for (;;) {
-      FT bv = hv[0];
-      int bl = 0;
-#pragma unroll
-      for (int s = 1; s < ML; s++)
-        if (hv[s] < bv) { bv = hv[s]; bl = s; }
-      if (bv == inf) break;
-      u32 bid = hid[0];
-      int bp = hp[0];
-#pragma unroll
-      for (int s = 1; s < ML; s++)
-        if (s == bl) { bid = hid[s]; bp = hp[s]; }
-      if (bid != last_id || out == 0) {
-        if (bv == last_v && out > 0) tie = true;                  // equal distance, different id, earlier one kept
-        if (out == k) break;                                      // the first dropped entry has been looked at
-        od[out] = bv;
-        oi[out] = bid;
-        out++;
-        last_id = bid;
-        last_v = bv;
-      }
-      // advance list bl
-      bp++;
-      FT nv = inf;
-      u32 ni = sentinel;
-      const int lim = a.admit[bl];
-      if (bp < lim) { nv = rd[bl * k + bp]; ni = ri[bl * k + bp]; }
-#pragma unroll
-      for (int s = 0; s < ML; s++)
-        if (s == bl) { hv[s] = nv; hid[s] = ni; hp[s] = bp; }
-    }
-    // prefix corner: the largest admitted entry dies if its id sits in the first slot
-    // outside the prefix and no admitted entry is infinite
-    if (a.corner_slot >= 0) {
-      bool any_inf = false;
-      FT max_v = -inf;
-      u32 max_id = sentinel;
-      for (int s = 0; s < NS; s++) {
-        int e = a.admit[s] - 1;
-        while (e >= 0 && rd[s * k + e] == inf) { any_inf = true; e--; }
-        if (e >= 0 && rd[s * k + e] > max_v) { max_v = rd[s * k + e]; max_id = ri[s * k + e]; }
-      }
-      if (!any_inf && out > 0) {
-        const u32 cid = ri[a.corner_slot * k + a.corner_pos];
-        if (cid == max_id && oi[out - 1] == cid) out--;           // the largest entry is the last one kept
-      }
-    }
-    for (int e = out; e < k; e++) { od[e] = inf; oi[e] = sentinel; }
-    if (tie && ties.rows) tie_report(ties, (u32)(x0 + tid));
+  for (int s = 0; s < ML; s++) {
+    const bool on = s < NS && a.admit[s] > 0;
+    hv[s] = on ? rd[s * k] : inf;
+    hp[s] = 0;
   }
-  __syncthreads();
-  // ---- coalesced copy-out of the pts output rows
-  for (int e = tid; e < pts * k; e += PT) {
-    const int p = e / k, z = e - p * k;
-    out_ids[(x0 + p) * (size_t)k + z] = sm[(size_t)p * row_words + off_oi + z];
-    out_dist[(x0 + p) * (size_t)k + z] = *reinterpret_cast<const FT *>(sm + (size_t)p * row_words + off_od + z * FW);
+  int out = 0, last_l = 0, last_p = 0;
+  FT last_v = -inf;
+  bool tie = false;
+  for (;;) {
+    FT bv = hv[0];
+    int bl = 0;
+#pragma unroll
+    for (int s = 1; s < ML; s++)
+      if (hv[s] < bv) { bv = hv[s]; bl = s; }
+    if (bv == inf) break;
+    int bp = hp[0];
+#pragma unroll
+    for (int s = 1; s < ML; s++)
+      if (s == bl) bp = hp[s];
+    bool dup = false;
+    if (out > 0 && bv == last_v) {                                // same id again, or an exact tie
+      dup = id_of(bl, bp) == id_of(last_l, last_p);
+      if (!dup) tie = true;                                       // earlier one kept (or the k-th vs the first dropped)
+    }
+    if (!dup) {
+      if (out == k) break;                                        // the first dropped entry has been looked at
+      out_dist[x * (size_t)k + out] = bv;
+      code[out] = (unsigned short)((bl << 8) | bp);
+      out++;
+      last_l = bl; last_p = bp; last_v = bv;
+    }
+    // advance list bl
+    bp++;
+    FT nv = inf;
+    if (bp < a.admit[bl]) nv = rd[bl * k + bp];
+#pragma unroll
+    for (int s = 0; s < ML; s++)
+      if (s == bl) { hv[s] = nv; hp[s] = bp; }
   }
+  // prefix corner: the largest admitted entry dies if its id sits in the first slot
+  // outside the prefix and no admitted entry is infinite; as the largest of everything it can
+  // only be the last entry kept
+  if (a.corner_slot >= 0 && out > 0) {
+    bool any_inf = false;
+    FT max_v = -inf;
+    int max_l = 0, max_p = 0;
+    for (int s = 0; s < NS; s++) {
+      int e = a.admit[s] - 1;
+      while (e >= 0 && rd[s * k + e] == inf) { any_inf = true; e--; }
+      if (e >= 0 && rd[s * k + e] > max_v) { max_v = rd[s * k + e]; max_l = s; max_p = e; }
+    }
+    if (!any_inf) {
+      const u32 cid = id_of(a.corner_slot, a.corner_pos);
+      if (cid == id_of(max_l, max_p) && id_of(last_l, last_p) == cid) out--;
+    }
+  }
+  for (int e = 0; e < out; e++) out_ids[x * (size_t)k + e] = id_of(code[e] >> 8, code[e] & 255);
+  for (int e = out; e < k; e++) { out_dist[x * (size_t)k + e] = inf; out_ids[x * (size_t)k + e] = sentinel; }
+  if (tie && ties.rows) tie_report(ties, (u32)x);
 }
 
 // Literal row: the n_lists lists of a point side by side (k*n_lists slots), the reference's
@@ -410,9 +402,9 @@ extern "C" void annb_merge_lists(const u32 *lists_ids, const FT *lists_dist, int
     int live = 0;
     for (int i = 0; i < ta.n_src; i++) live += ta.admit[i] > 0;
     const int FW = (int)(sizeof(FT) / 4);
-    int row_words = (ta.n_src * (int)k + (int)k) * (1 + FW);
+    int row_words = ta.n_src * (int)k * FW + ((int)k + 1) / 2;     // distances + 16-bit codes of the kept entries
+    row_words = (row_words + 3) & ~3;
     row_words += (16 - (row_words & 31) + 32) & 31;                // = 16 mod 32: two points never share a bank phase
-    if ((row_words & 3) != 0) row_words = (row_words + 3) & ~3;
     const size_t tsmem = (size_t)row_words * 4 * 64;
     if (fits && live >= 1 && live <= 16 && ta.n_src <= 17 && tsmem <= 200 * 1024) {
       // the corner list (admit 0) is staged but never a merge source; sources must sit in slots < ML

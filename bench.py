@@ -623,7 +623,7 @@ def main():
     sc_s = mean_stage["supercharge"] / 1e3
     roofline_hbm = {"kernel": "supercharge kernels (S5, all row chunks of one step)", "bound": "hbm",
                     "achieved": sc_bytes / sc_s / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": sc_bytes / sc_s / 1e9 / peak, "traffic": traffic.get("supercharge"),
+                    "frac": sc_bytes / sc_s / 1e9 / peak, "traffic": traffic.get("supercharge_screen_kernel"),
                     "share_of_device_time": mean_stage["supercharge"] / dev_mean}
     # --- the whole step against HBM (SURVEY 8.D's per-run byte model; w = sizeof ftype, B = buckets)
     ds = int(np.ceil(np.log2((np.float32(n) if dtype == np.float32 else np.float64(n)) / k)))
