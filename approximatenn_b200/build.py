@@ -16,7 +16,7 @@ CUDA_HOME = os.path.dirname(os.path.dirname(os.path.realpath(NVCC)))
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 CU_SOURCES = ["annb_prepare.cu", "annb_leaf.cu", "annb_finish.cu", "annb_query.cu", "annb_probe.cu"]
-C_SOURCES = ["ann_host.c", "ann_results.c", "ann_ingest.c", "ann_query.c", "ann_dist.c", "ann_save_io.c"]
+C_SOURCES = ["ann_host.c", "ann_results.c", "ann_ingest.c", "ann_query.c", "ann_dist.c", "ann_save_io.c", "ann_multi.c"]
 HEADERS = [os.path.join(INCLUDE, h) for h in os.listdir(INCLUDE)] + [
     os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".h", ".cuh"))]
 

@@ -31,7 +31,7 @@ typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { NCCL_OK = 0, NCCL_UINT8 = 1 };
 
-static struct {
+static __thread struct {
   void *lib;
   int (*GetUniqueId)(ncclUniqueId *);
   int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);

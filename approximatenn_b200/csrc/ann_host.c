@@ -46,7 +46,7 @@ void annh_fatal(const char *fmt, const char *detail) {
 typedef struct hook { void (*f)(void); struct hook *next; } hook;
 #define ANNH_MAX_SPANS 1024
 
-static struct {
+static __thread struct {
   int ready;
   int device;
   cudaStream_t stream;
@@ -63,8 +63,17 @@ static struct {
   int spans;
 } G;
 
+static void gpu_init_device(int forced_device);
+
 void gpu_init(void) {
   if (G.ready) return;
+  if (annh_multi_gpus() > 1 && !annh_multi_in_worker()) { annh_multi_start(); return; }
+  gpu_init_device(-1);
+}
+
+void annh_gpu_init_on(int device) { if (!G.ready) gpu_init_device(device); }
+
+static void gpu_init_device(int forced_device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
@@ -72,7 +81,8 @@ void gpu_init(void) {
                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
   const char *env = getenv("ANN_B200_DEVICE");
   int dev = 0;
-  if (env && *env) dev = atoi(env);
+  if (forced_device >= 0) dev = forced_device;
+  else if (env && *env) dev = atoi(env);
   else CK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= count) annh_fatal("ANN_B200_DEVICE=%s is out of range", env ? env : "?");
   CK(cudaSetDevice(dev));
@@ -92,6 +102,11 @@ void register_cleanup(void (*f)(void)) {
 }
 
 void gpu_cleanup(void) {
+  if (annh_multi_gpus() > 1 && !annh_multi_in_worker()) annh_multi_stop();
+  annh_gpu_cleanup_impl();
+}
+
+void annh_gpu_cleanup_impl(void) {
   if (!G.ready) return;
   while (G.hooks) {
     hook *h = G.hooks;
@@ -217,6 +232,21 @@ static void draw_transform(host_transform *t, size_t rots_b, size_t len_b, size_
 
 static void free_transform(host_transform *t) {
   free(t->ci); free(t->cj); free(t->ang); free(t->perm_b); free(t->perm_ai);
+}
+
+void *annh_draw_transforms(size_t n, size_t k, size_t d, int tries, size_t rots_before, size_t rot_len_before,
+                           size_t rots_after, size_t rot_len_after) {
+  size_t d_short, d_max;
+  annh_params(n, k, d, &d_short, &d_max);
+  host_transform *tf = malloc(sizeof(host_transform) * (size_t)tries);
+  for (int t = 0; t < tries; t++)
+    draw_transform(tf + t, rots_before, rot_len_before, rots_after, rot_len_after, d_short, d, d_max);
+  return tf;
+}
+void annh_free_transforms(void *p, int tries) {
+  host_transform *tf = p;
+  for (int t = 0; t < tries; t++) free_transform(tf + t);
+  free(tf);
 }
 
 /* ---- the d_short x d projection matrix of one transform (save->bases), alg.c:189-217 ----
@@ -365,6 +395,16 @@ static annh_tables *save_tables_begin(save_t *save, const annb_u32 *h_tm, size_t
 size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries,
                     size_t rots_before, size_t rot_len_before, size_t rots_after,
                     size_t rot_len_after, save_t *save, ftype **dists_o) {
+  if (annh_multi_gpus() > 1 && !annh_multi_in_worker())
+    return annh_multi_precomp(n, k, d, points, tries, rots_before, rot_len_before, rots_after, rot_len_after,
+                              save, dists_o);
+  return annh_precomp_impl(n, k, d, points, tries, rots_before, rot_len_before, rots_after, rot_len_after, save,
+                           dists_o, NULL);
+}
+
+size_t *annh_precomp_impl(size_t n, size_t k, size_t d, const ftype *points, int tries,
+                          size_t rots_before, size_t rot_len_before, size_t rots_after,
+                          size_t rot_len_after, save_t *save, ftype **dists_o, const annh_call_ctx *ctx) {
   double hp_start = now_ms(), hp_last = hp_start;
   gpu_init();
   CK(cudaSetDevice(G.device));
@@ -378,7 +418,8 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   cudaStream_t st = G.stream;
 
   /* sharding (ann_dist.c): rank r owns tries t = r, r+R, ... and the rows [row_lo, row_hi)  */
-  const int R = annh_dist_world(), rank = annh_dist_rank();
+  const int single = ctx && ctx->force_single;
+  const int R = single ? 1 : annh_dist_world(), rank = single ? 0 : annh_dist_rank();
   const int sharded = R > 1;
   size_t row_lo = 0, row_hi = n;
   if (sharded) annb200_dist_slice(n, rank, R, &row_lo, &row_hi);
@@ -388,13 +429,14 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   if (sharded && T > 64) annh_fatal("%s", "more than 64 tries in sharded mode");
   const int full_result = !sharded || annh_dist_gather_results() || save != NULL;
   const size_t out_rows = full_result ? n : my_rows;
-  annh_egress *eg = annh_egress_begin(out_rows, k, dists_o != NULL, save != NULL, G.device);
+  annh_egress *eg = annh_egress_begin(out_rows, k, dists_o != NULL, save != NULL, G.device, ctx ? &ctx->out : NULL);
 
   HP("egress_begin");
   /* 1. transforms: ALL tries are drawn before any compute (alg.c:388-392), on every rank   */
-  host_transform *tf = malloc(sizeof(host_transform) * T);
-  for (size_t t = 0; t < T; t++)
-    draw_transform(tf + t, rots_before, rot_len_before, rots_after, rot_len_after, d_short, d, d_max);
+  host_transform *tf = ctx && ctx->transforms ? ctx->transforms : malloc(sizeof(host_transform) * T);
+  if (!(ctx && ctx->transforms))
+    for (size_t t = 0; t < T; t++)
+      draw_transform(tf + t, rots_before, rot_len_before, rots_after, rot_len_after, d_short, d, d_max);
   size_t *own = malloc(sizeof(size_t) * (Tl + 1));             /* global index of owned try j */
   for (size_t t = 0, j = 0; t < T; t++)
     if (annb200_dist_try_owner((int)t, R) == rank) own[j++] = t;
@@ -427,7 +469,7 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   desc.tries = (int)Tl;
   desc.inv_sqrt2 = 1 / sqrt(2.0);
   const size_t list_bytes = n * k * (4 + w);                   /* one per-try list      */
-  const size_t np = annh_dist_padded_rows(n);                  /* rows of all-gathered arrays */
+  const size_t np = sharded ? annh_dist_padded_rows(n) : n;    /* rows of all-gathered arrays */
   const size_t scratch_bytes = annb_leaf_scratch_bytes(n, d, d_short, k);
   size_t fixed = pad256(np * d * w) + pad256(n * d * w) + pad256(d * w) + pad256(Tl * n * 4 + 4) +
                  pad256(buckets * 4) + pad256((buckets + 1) * 4) + pad256(n * 4) * 2 +
@@ -727,8 +769,11 @@ size_t *precomp_gpu(size_t n, size_t k, size_t d, const ftype *points, int tries
   free(dtab); free(h_tm_all);
   if (save) save->graph = graph_copy;                           /* alg.c:428-432: two separate copies */
   if (adopt) annh_index_adopt_finish(save, points, dX, dmean, dout_ids);
-  for (size_t t = 0; t < T; t++) free_transform(tf + t);
-  free(tf); free(own); free(h_idx); free(h_cs); free(h_permb); free(h_pick);
+  if (!(ctx && ctx->transforms)) {
+    for (size_t t = 0; t < T; t++) free_transform(tf + t);
+    free(tf);
+  }
+  free(own); free(h_idx); free(h_cs); free(h_permb); free(h_pick);
   return result;
 }
 

@@ -38,7 +38,12 @@ void annh_set_timing(int on);
 /* result egress (ann_results.c): malloc()ed result arrays filled chunk by chunk through a
  * pinned staging buffer while later chunks are still being computed                        */
 typedef struct annh_egress annh_egress;
-annh_egress *annh_egress_begin(size_t rows, size_t k, int want_dist, int want_second_ids, int device);
+/* into != NULL: the rows of this call go to caller-provided arrays (ids, and dist / ids2 when
+ * wanted) instead of fresh malloc()s — the single-process multi-GPU mode hands every device
+ * its slice of ONE result array this way                                                     */
+typedef struct { size_t *ids; ftype *dist; size_t *ids2; } annh_egress_target;
+annh_egress *annh_egress_begin(size_t rows, size_t k, int want_dist, int want_second_ids, int device,
+                               const annh_egress_target *into);
 int annh_egress_chunks(const annh_egress *e);          /* how many row chunks to produce    */
 void annh_egress_chunk(annh_egress *e, size_t r0, size_t r1, const void *dev_ids_u32,
                        const void *dev_dist, void *producer_stream);
@@ -75,6 +80,34 @@ void annh_index_adopt_finish(const save_t *s, const ftype *host_points, const ft
 
 /* drops any device-resident copy of `save` kept for query_gpu (called by free_save)      */
 void annh_forget_save(const save_t *save);
+
+/* ---- single-process multi-GPU mode (ann_multi.c): ANN_B200_GPUS=N ---------------------------
+ * One worker thread per device; all library state is per thread, so a worker is exactly what a
+ * rank process is in the torchrun mode.  The public entry points forward to the workers.      */
+typedef struct {
+  void *transforms;            /* the tries' transforms, drawn once by the caller (annh_draw_transforms) */
+  int force_single;            /* run the whole problem on this device although a world exists      */
+  annh_egress_target out;      /* this rank's slice of the shared result arrays (ids == NULL: malloc) */
+} annh_call_ctx;
+void *annh_draw_transforms(size_t n, size_t k, size_t d, int tries, size_t rots_before, size_t rot_len_before,
+                           size_t rots_after, size_t rot_len_after);
+void annh_free_transforms(void *tf, int tries);
+size_t *annh_precomp_impl(size_t n, size_t k, size_t d, const ftype *points, int tries, size_t rots_before,
+                          size_t rot_len_before, size_t rots_after, size_t rot_len_after, save_t *save,
+                          ftype **dists_o, const annh_call_ctx *ctx);
+size_t *annh_query_impl(const save_t *save, const ftype *points, size_t ycnt, const ftype *y, ftype **dists_o);
+void annh_forget_save_impl(const save_t *save);
+void annh_gpu_init_on(int device);        /* gpu_init() of the calling thread on a given device */
+void annh_gpu_cleanup_impl(void);
+int annh_multi_gpus(void);                /* N of ANN_B200_GPUS (clamped to the devices present), 1 = off */
+int annh_multi_in_worker(void);
+void annh_multi_start(void);
+void annh_multi_stop(void);
+size_t *annh_multi_precomp(size_t n, size_t k, size_t d, const ftype *points, int tries, size_t rots_before,
+                           size_t rot_len_before, size_t rots_after, size_t rot_len_after, save_t *save,
+                           ftype **dists_o);
+size_t *annh_multi_query(const save_t *save, const ftype *points, size_t ycnt, const ftype *y, ftype **dists_o);
+void annh_multi_forget(const save_t *save);
 
 #ifdef __cplusplus
 }

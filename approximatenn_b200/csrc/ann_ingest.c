@@ -32,7 +32,7 @@
 #define INGEST_SLOTS (INGEST_MAX_THREADS * INGEST_PER_THREAD)
 #define INGEST_CHUNK ((size_t)4 << 20)       /* bytes per slot                            */
 
-static struct {
+static __thread struct {
   char *ring;                                /* INGEST_SLOTS * INGEST_CHUNK pinned bytes   */
   cudaStream_t stream[INGEST_MAX_THREADS];
   cudaEvent_t slot_free[INGEST_SLOTS];

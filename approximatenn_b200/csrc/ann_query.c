@@ -60,8 +60,9 @@ typedef struct {
   size_t cap_points, cap_mean, cap_bases, cap_graph, *cap_tab, cap_tries;
 } device_index;
 
-static device_index IDX;
-static int cleanup_registered;
+/* per host thread = per device (ann_multi.c runs one worker thread per GPU) */
+static __thread device_index IDX;
+static __thread int cleanup_registered;
 
 static uint64_t mix(uint64_t h, uint64_t v) {
   h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
@@ -138,8 +139,12 @@ static void reserve_index(size_t n, size_t k, size_t d_short, size_t d, size_t t
   }
 }
 
-void annh_forget_save(const save_t *save) {
+void annh_forget_save_impl(const save_t *save) {
   if (IDX.live && IDX.graph_key == save->graph) drop_index();
+}
+void annh_forget_save(const save_t *save) {
+  if (annh_multi_gpus() > 1 && !annh_multi_in_worker()) annh_multi_forget(save);
+  else annh_forget_save_impl(save);
 }
 
 /* include/annb200_io.h: callers that rewrite `points` or a save_t IN PLACE (same addresses, same
@@ -213,6 +218,12 @@ void annh_index_adopt_finish(const save_t *s, const ftype *host_points, const ft
 
 size_t *query_gpu(const save_t *save, const ftype *points, size_t ycnt, const ftype *y,
                   ftype **dists_o) {
+  if (annh_multi_gpus() > 1 && !annh_multi_in_worker()) return annh_multi_query(save, points, ycnt, y, dists_o);
+  return annh_query_impl(save, points, ycnt, y, dists_o);
+}
+
+size_t *annh_query_impl(const save_t *save, const ftype *points, size_t ycnt, const ftype *y,
+                        ftype **dists_o) {
   gpu_init();
   cudaStream_t st = (cudaStream_t)annh_stream();
   const char *qenv = getenv("ANN_B200_HOSTPROF");
@@ -234,7 +245,7 @@ size_t *query_gpu(const save_t *save, const ftype *points, size_t ycnt, const ft
     build_index(save, points, fp);
   QP("fingerprint+index");
 
-  annh_egress *eg = annh_egress_begin(ycnt, k, dists_o != NULL, 0, annh_device());
+  annh_egress *eg = annh_egress_begin(ycnt, k, dists_o != NULL, 0, annh_device(), NULL);
   const size_t scratch_bytes = ycnt * 4 + 1024 + ((size_t)64 << 20);
   size_t need = (ycnt * d * w + 256) + (T * ycnt * 4 + 256) + 2 * (ycnt * k * 4 + 256) +
                 2 * (ycnt * k * w + 256) + scratch_bytes + 4096;

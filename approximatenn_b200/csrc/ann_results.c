@@ -55,7 +55,7 @@ struct annh_egress {
   egress_chunk chunk[EGRESS_MAX_CHUNKS];
 };
 
-static struct {
+static __thread struct {
   void *stage;
   size_t stage_bytes;
   cudaStream_t copy;
@@ -130,12 +130,20 @@ static void *egress_worker(void *p) {
   return NULL;
 }
 
-annh_egress *annh_egress_begin(size_t rows, size_t k, int want_dist, int want_second_ids, int device) {
+annh_egress *annh_egress_begin(size_t rows, size_t k, int want_dist, int want_second_ids, int device,
+                               const annh_egress_target *into) {
   annh_egress *e = calloc(1, sizeof *e);
   e->rows = rows; e->k = k; e->device = device;
-  e->ids = malloc(sizeof(size_t) * rows * k);
-  e->dist = want_dist ? malloc(sizeof(ftype) * rows * k) : NULL;
-  e->ids2 = want_second_ids ? malloc(sizeof(size_t) * rows * k) : NULL;
+  if (into && into->ids) {
+    e->ids = into->ids;
+    e->dist = want_dist ? into->dist : NULL;
+    e->ids2 = want_second_ids ? into->ids2 : NULL;
+  } else {
+    const size_t cells = rows * k > 0 ? rows * k : 1;
+    e->ids = malloc(sizeof(size_t) * cells);
+    e->dist = want_dist ? malloc(sizeof(ftype) * cells) : NULL;
+    e->ids2 = want_second_ids ? malloc(sizeof(size_t) * cells) : NULL;
+  }
   if (!e->ids || (want_dist && !e->dist) || (want_second_ids && !e->ids2)) annh_fatal("%s", "out of host memory for the result arrays");
   if (!S.ready) {
     CK(cudaStreamCreateWithFlags(&S.copy, cudaStreamNonBlocking));
@@ -263,7 +271,7 @@ struct annh_tables {
   pthread_cond_t cv;
   int submitted, closed;
 };
-static struct { annb_u32 *stage; size_t bytes; } TS;
+static __thread struct { annb_u32 *stage; size_t bytes; } TS;
 
 static void *tables_worker(void *p) {
   struct annh_tables *tb = *(struct annh_tables **)p;        /* first member of the argument record */

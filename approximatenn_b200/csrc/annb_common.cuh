@@ -26,7 +26,7 @@ static inline int annb_debug_sync() {
 
 #define LAUNCH_CHECK(what)                                                              \
   do {                                                                                  \
-    annb_g_launches++;                                                                  \
+    __sync_fetch_and_add(&annb_g_launches, 1ul);                                        \
     cudaError_t e_ = cudaGetLastError();                                                \
     if (e_ == cudaSuccess && annb_debug_sync()) {                                       \
       fprintf(stderr, "[debug-sync] %s launched\n", what);                              \

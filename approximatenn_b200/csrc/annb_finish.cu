@@ -409,7 +409,7 @@ extern "C" void annb_merge_lists(const u32 *lists_ids, const FT *lists_dist, int
     if (fits && live >= 1 && live <= 16 && ta.n_src <= 17 && tsmem <= 200 * 1024) {
       // the corner list (admit 0) is staged but never a merge source; sources must sit in slots < ML
       const bool big = live > 8 || ta.n_src > 8;
-      static size_t configured[2] = {0, 0};
+      static thread_local size_t configured[2] = {0, 0};
       if (tsmem > configured[big]) {
         if (big) RT_CHECK(cudaFuncSetAttribute(merge_lists_thread_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         else RT_CHECK(cudaFuncSetAttribute(merge_lists_thread_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -607,7 +607,7 @@ static void launch_tile(annb_stream stream, const FT *sp, const u32 *order, cons
                         const u32 *tmax, size_t n, size_t buckets, int d_short, int k, u32 *ids,
                         FT *dist, TieList flags, const u32 *bucket_list, const u32 *bucket_count) {
   size_t smem = TileSmem<D, KC, B>::per_warp * TILE_WARPS;
-  static bool configured = false;
+  static thread_local bool configured = false;   // per host thread = per device
   if (!configured) {
     RT_CHECK(cudaFuncSetAttribute(leaf_topk_tile_kernel<D, KC, B, REGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
@@ -793,7 +793,7 @@ static void launch_screen(annb_stream stream, const FT *sp, const FT *mean, void
   if (ct > 1032) ct = 1032;
   if (ct < screen_min_ct(ScreenOverlay<D>::bytes)) ct = screen_min_ct(ScreenOverlay<D>::bytes);
   size_t smem = screen_smem_bytes(ct);
-  static bool configured = false;
+  static thread_local bool configured = false;   // per host thread = per device
   if (!configured) {
     RT_CHECK(cudaFuncSetAttribute(leaf_screen_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)screen_smem_bytes(1032)));
     configured = true;

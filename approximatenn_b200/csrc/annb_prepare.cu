@@ -382,16 +382,16 @@ static bool launch_hash_const(const FT *points, const FT *mean, const annb_trans
   if (smem > 200 * 1024 || d + 2 * planes_b >= 0xffff || planes_all > (size_t)HT_OPS || ds > (size_t)HT_PICK) return false;
   size_t batch = t->tries;
   while (batch > 1 && (batch * DM > (size_t)HT_GSRC || batch * planes_all > (size_t)HT_OPS || batch * ds > (size_t)HT_PICK)) batch--;
-  static bool configured = false;
+  static thread_local bool configured = false;   // per host thread = per device
   if (!configured) {
     RT_CHECK(cudaFuncSetAttribute(hash_points_const_kernel<DM, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  static unsigned short *h_gsrc = NULL, *h_pick = NULL;
-  static HashOp *h_ops = NULL;
-  static FT *h_cs = NULL;
-  static unsigned *latest = NULL;
-  static size_t latest_cap = 0;
+  static thread_local unsigned short *h_gsrc = NULL, *h_pick = NULL;
+  static thread_local HashOp *h_ops = NULL;
+  static thread_local FT *h_cs = NULL;
+  static thread_local unsigned *latest = NULL;
+  static thread_local size_t latest_cap = 0;
   if (!h_gsrc) {                                               // pinned: the async copies below read them later
     RT_CHECK(cudaMallocHost((void **)&h_gsrc, sizeof(unsigned short) * HT_GSRC));
     RT_CHECK(cudaMallocHost((void **)&h_pick, sizeof(unsigned short) * HT_PICK));
@@ -443,7 +443,7 @@ static bool launch_hash_reg(const FT *points, const FT *mean, const annb_transfo
   constexpr int TP = 128;
   size_t smem = (t->d + DM) * (size_t)(TP + 1) * sizeof(FT);
   if (smem > 200 * 1024) return false;
-  static bool configured = false;
+  static thread_local bool configured = false;   // per host thread = per device
   if (!configured) {
     RT_CHECK(cudaFuncSetAttribute(hash_points_reg_kernel<DM, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
@@ -501,7 +501,7 @@ extern "C" void annb_hash_points(const FT *points, const FT *mean, const annb_tr
   size_t tiles = (t->n + HASH_TP - 1) / HASH_TP;
   size_t need = hash_plane_bytes(t);
   if (need <= HASH_SMEM_LIMIT) {
-    static size_t configured = 0;
+    static thread_local size_t configured = 0;
     if (need > configured) {
       RT_CHECK(cudaFuncSetAttribute(hash_points_kernel<HASH_TP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)HASH_SMEM_LIMIT));
