@@ -32,13 +32,14 @@
 #define INGEST_SLOTS (INGEST_MAX_THREADS * INGEST_PER_THREAD)
 #define INGEST_CHUNK ((size_t)4 << 20)       /* bytes per slot                            */
 
-static __thread struct {
+struct ingest_state {
   char *ring;                                /* INGEST_SLOTS * INGEST_CHUNK pinned bytes   */
   cudaStream_t stream[INGEST_MAX_THREADS];
   cudaEvent_t slot_free[INGEST_SLOTS];
   cudaEvent_t done[INGEST_MAX_THREADS];
   int ready;
-} I;
+};
+static __thread struct ingest_state I;       /* per calling thread = per device (ann_multi.c) */
 
 void annh_ingest_release(void) {
   if (!I.ready) return;
@@ -48,7 +49,7 @@ void annh_ingest_release(void) {
   memset(&I, 0, sizeof I);
 }
 
-typedef struct { const char *src; char *dst; size_t bytes; int me, device, threads; } ingest_job;
+typedef struct { const char *src; char *dst; size_t bytes; int me, device, threads; struct ingest_state *st; } ingest_job;
 
 /* One memcpy thread moves ~6-8 GB/s into the pinned ring and PCIe 5 takes ~54 GB/s, so the
  * copy needs about eight of them; the count follows the cores the box has (the egress
@@ -74,16 +75,16 @@ static void *ingest_worker(void *p) {
   for (size_t c = j->me; c < chunks; c += j->threads, use++) {
     int slot = j->me * INGEST_PER_THREAD + (use % INGEST_PER_THREAD);
     size_t off = c * INGEST_CHUNK, len = j->bytes - off < INGEST_CHUNK ? j->bytes - off : INGEST_CHUNK;
-    char *stage = I.ring + (size_t)slot * INGEST_CHUNK;
-    if (cudaEventSynchronize(I.slot_free[slot]) != cudaSuccess) exit(1);   /* DMA of its last use done */
+    char *stage = j->st->ring + (size_t)slot * INGEST_CHUNK;
+    if (cudaEventSynchronize(j->st->slot_free[slot]) != cudaSuccess) exit(1);   /* DMA of its last use done */
     memcpy(stage, j->src + off, len);
-    if (cudaMemcpyAsync(j->dst + off, stage, len, cudaMemcpyHostToDevice, I.stream[j->me]) != cudaSuccess ||
-        cudaEventRecord(I.slot_free[slot], I.stream[j->me]) != cudaSuccess) {
+    if (cudaMemcpyAsync(j->dst + off, stage, len, cudaMemcpyHostToDevice, j->st->stream[j->me]) != cudaSuccess ||
+        cudaEventRecord(j->st->slot_free[slot], j->st->stream[j->me]) != cudaSuccess) {
       fprintf(stderr, "approximatenn_b200: staged upload failed: %s\n", cudaGetErrorString(cudaGetLastError()));
       exit(1);
     }
   }
-  if (cudaEventRecord(I.done[j->me], I.stream[j->me]) != cudaSuccess) exit(1);
+  if (cudaEventRecord(j->st->done[j->me], j->st->stream[j->me]) != cudaSuccess) exit(1);
   return NULL;
 }
 
@@ -123,6 +124,7 @@ void annh_ingest(void *dst, const void *src, size_t bytes, void *consumer, int d
   for (int i = 0; i < nt; i++) {
     job[i].src = src; job[i].dst = dst; job[i].bytes = bytes; job[i].me = i; job[i].device = device;
     job[i].threads = nt;
+    job[i].st = &I;
     if (pthread_create(&th[i], NULL, ingest_worker, &job[i]) != 0) annh_fatal("%s", "pthread_create failed");
   }
   for (int i = 0; i < nt; i++) {

@@ -264,6 +264,7 @@ struct annh_tables {
   size_t *cells;               /* [tries] */
   size_t *at;                  /* [tries] offset (cells) into the staging buffer */
   size_t **host;               /* [tries] destination arrays (owned by the caller's save_t) */
+  const annb_u32 *stage;       /* the owning thread's pinned staging (TS is per thread)     */
   cudaEvent_t *done;           /* [tries] */
   pthread_t th[TABLE_THREADS];
   struct { struct annh_tables *tb; int idx; } arg[TABLE_THREADS];
@@ -288,7 +289,7 @@ static void *tables_worker(void *p) {
       exit(1);
     }
     size_t lo = tb->cells[t] * (size_t)me / tb->nthreads, hi = tb->cells[t] * (size_t)(me + 1) / tb->nthreads;
-    const annb_u32 *src = TS.stage + tb->at[t];
+    const annb_u32 *src = tb->stage + tb->at[t];
     size_t *dst = tb->host[t];
     for (size_t i = lo; i < hi; i++) dst[i] = src[i];
   }
@@ -315,6 +316,7 @@ annh_tables *annh_tables_begin(int tries, const size_t *cells, size_t **host_tab
     CK(cudaMallocHost((void **)&TS.stage, total * 4 + 256));
     TS.bytes = total * 4 + 256;
   }
+  tb->stage = TS.stage;
   if (!S.ready) {
     CK(cudaStreamCreateWithFlags(&S.copy, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&S.produced, cudaEventDisableTiming));

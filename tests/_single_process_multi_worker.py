@@ -31,6 +31,18 @@ def main():
             ok &= good
         nod = gpu.precomp(pts, k, tries, want_dists=False, seed=seed)
         ok &= np.array_equal(nod.ids, want.ids)
+    # a slice large enough for the staged (multi-threaded) upload inside every worker; sampled rows
+    from approximatenn_b200.api import srandom
+    n, d, k, tries = 300_000, 64, 16, 2
+    rng = np.random.default_rng(505)
+    pts = rng.standard_normal((n, d), dtype=np.float32)
+    sample = np.sort(rng.choice(n, size=48, replace=False))
+    got = gpu_backend(np.float32).precomp(pts, k, tries, seed=505)
+    srandom(505)
+    want_ids, want_d, _ = oracle.sampled_rows(oracle.restatement(np.float32), pts, k, tries, sample)
+    good = np.array_equal(got.ids[sample], want_ids) and same_bits(got.dists[sample], want_d)
+    print(f"float32 n={n} staged upload, sampled rows {'OK' if good else 'MISMATCH'}", flush=True)
+    ok &= good
     # save_t and query run on device 0
     rng = np.random.default_rng(9)
     pts = rng.standard_normal((6000, 32)).astype(np.float32)
