@@ -54,6 +54,10 @@ typedef struct {
   uint64_t fingerprint;
   ftype *d_points, *d_mean, *d_bases;
   annb_u32 *d_graph;
+  void *d_points16, *d_nrm;    /* fp16 copy of the points + norms for the screened candidate rows */
+  unsigned *d_scale;
+  size_t cap_points16, cap_nrm, cap_scale;
+  int screened;
   annb_u32 **d_tab;            /* host array of device pointers to the 32-bit tables */
   /* capacities in bytes: the buffers are grow-only and survive a dropped index, because
    * cudaMalloc/cudaFree of a few hundred MB cost more than a whole query                 */
@@ -111,6 +115,9 @@ static void release_index(void) {
   if (IDX.d_mean) CK(cudaFree(IDX.d_mean));
   if (IDX.d_bases) CK(cudaFree(IDX.d_bases));
   if (IDX.d_graph) CK(cudaFree(IDX.d_graph));
+  if (IDX.d_points16) CK(cudaFree(IDX.d_points16));
+  if (IDX.d_nrm) CK(cudaFree(IDX.d_nrm));
+  if (IDX.d_scale) CK(cudaFree(IDX.d_scale));
   for (size_t t = 0; t < IDX.cap_tries; t++)
     if (IDX.d_tab[t]) CK(cudaFree(IDX.d_tab[t]));
   free(IDX.d_tab);
@@ -127,6 +134,12 @@ static void reserve_index(size_t n, size_t k, size_t d_short, size_t d, size_t t
   reserve((void **)&IDX.d_mean, &IDX.cap_mean, d * w);
   reserve((void **)&IDX.d_bases, &IDX.cap_bases, (tries * d_short * d + 1) * w);
   reserve((void **)&IDX.d_graph, &IDX.cap_graph, n * k * 4);
+  IDX.screened = annb_query_screen_applies(d, k);
+  if (IDX.screened) {
+    reserve(&IDX.d_points16, &IDX.cap_points16, n * d * 2);
+    reserve(&IDX.d_nrm, &IDX.cap_nrm, n * 8);
+    reserve((void **)&IDX.d_scale, &IDX.cap_scale, 256);
+  }
   if (tries > IDX.cap_tries) {
     IDX.d_tab = realloc(IDX.d_tab, tries * sizeof(annb_u32 *));
     IDX.cap_tab = realloc(IDX.cap_tab, tries * sizeof(size_t));
@@ -156,6 +169,13 @@ static void upload_narrow(const size_t *host, size_t count, annb_u32 *dst, size_
   annb_narrow_ids(tmp, count, dst, st);
 }
 
+/* fp16 copy + norms of the indexed points (device-resident points and means must be enqueued) */
+static void prepare_screen(cudaStream_t st) {
+  if (!IDX.screened) return;
+  annb_screen_scale(IDX.d_points, IDX.d_mean, IDX.n, IDX.d, IDX.d_scale, st);
+  annb_screen_prep_points(IDX.d_points, IDX.d_mean, IDX.n, IDX.d, IDX.d_scale, IDX.d_points16, IDX.d_nrm, st);
+}
+
 static void build_index(const save_t *s, const ftype *points, uint64_t fp) {
   cudaStream_t st = (cudaStream_t)annh_stream();
   const size_t w = sizeof(ftype), T = (size_t)s->tries, B = (size_t)1 << s->d_short;
@@ -171,6 +191,7 @@ static void build_index(const save_t *s, const ftype *points, uint64_t fp) {
   annh_ingest(IDX.d_points, points, s->n * s->d_long * w, st, annh_device());
   CK(cudaMemcpyAsync(IDX.d_mean, s->row_means, s->d_long * w, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(IDX.d_bases, s->bases, T * s->d_short * s->d_long * w, cudaMemcpyHostToDevice, st));
+  prepare_screen(st);
   upload_narrow(s->graph, s->n * s->k, IDX.d_graph, tmp, st);
   for (size_t t = 0; t < T; t++) upload_narrow(s->which_par[t], B * s->par_maxes[t], IDX.d_tab[t], tmp, st);
   CK(cudaStreamSynchronize(st));
@@ -209,6 +230,7 @@ void annh_index_adopt_finish(const save_t *s, const ftype *host_points, const ft
   CK(cudaMemcpyAsync(IDX.d_mean, dev_mean, s->d_long * w, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(IDX.d_bases, s->bases, (size_t)s->tries * s->d_short * s->d_long * w, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(IDX.d_graph, dev_graph, s->n * s->k * 4, cudaMemcpyDeviceToDevice, st));
+  prepare_screen(st);
   CK(cudaStreamSynchronize(st));
   IDX.graph_key = s->graph;
   IDX.points_key = host_points;
@@ -266,9 +288,11 @@ size_t *annh_query_impl(const save_t *save, const ftype *points, size_t ycnt, co
   QP("alloc+upload y");
   annb_query_hash(dq, IDX.d_mean, IDX.d_bases, ycnt, d, ds, (int)T, dsign, st);
   QP("query_hash");
+  annb_query_screen qs;
+  qs.points16 = IDX.d_points16; qs.nrm = IDX.d_nrm; qs.mean = IDX.d_mean; qs.scale_bits = IDX.d_scale;
   annb_query_rows(dq, IDX.d_points, (const annb_u32 *const *)IDX.d_tab, save->par_maxes, (int)T,
                   dsign, n, ycnt, d, ds, k, same_set, down_ids, down_dist, dscratch, scratch_bytes,
-                  dstatus, st);
+                  dstatus, IDX.screened ? &qs : NULL, st);
   QP("query_rows");
   int nch = annh_egress_chunks(eg);
   for (int c = 0; c < nch; c++) {

@@ -2,6 +2,10 @@
 // vectors, candidate rows out of the saved bucket tables, k best per query.  The final
 // supercharging step is annb_supercharge() (annb_finish.cu) with graph = save->graph.
 #include "annb_common.cuh"
+#ifdef USE_FLOAT
+#include <cuda_fp16.h>
+#include "annb_screen_common.cuh"
+#endif
 
 static __device__ unsigned long long query_literal_rows_dev;
 unsigned long long annb_query_literal_count(int reset) {
@@ -162,14 +166,29 @@ query_rows_kernel(const FT *__restrict__ y, const FT *__restrict__ points, Query
 #ifdef USE_FLOAT
 static constexpr int QBUF = 192;                                  // buffered candidate ids per warp
 
-template <int D>
+// With SCREEN (the index carries the fp16 copy of the points, annb_query_screen), every flush of
+// the id buffer first brackets its candidates against the CURRENT k-th best — the bracket and
+// the shuffle-free tensor-core operand layout of supercharge_screen_kernel, the query's fp16
+// words computed on the fly from (y - mean) * scale — and only the survivors get the exact
+// tree.  tau only shrinks, so a candidate dropped against the current tau could never have
+// entered the final list; the prefix-corner rule can only fire when nothing was dropped at
+// all (see annb_supercharge_screen.cuh), and then every candidate was measured exactly.
+struct QueryScreenDev {
+  const unsigned short *p16;
+  const float2 *nrm;
+  const float *mean;
+  const unsigned *scale_bits;
+};
+
+template <int D, bool SCREEN>
 __global__ void __launch_bounds__(256)
 query_rows_fast_kernel(const float *__restrict__ y, const float *__restrict__ points, QueryTables q,
                        const u32 *__restrict__ sign, size_t n,
                        size_t ycnt, int d_short, int k, int exclude_self, u32 *__restrict__ list_ids,
-                       float *__restrict__ list_dist, TieList ties) {
+                       float *__restrict__ list_dist, TieList ties, QueryScreenDev scr) {
   constexpr int LPC = D / 8, CPR = 32 / LPC;
-  __shared__ u32 s_buf[8][QBUF];
+  constexpr int KS2 = D >= 32 ? D / 32 : 1;
+  __shared__ __align__(16) u32 s_buf[8][QBUF + 16];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   size_t x = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (x >= ycnt) return;
@@ -183,11 +202,91 @@ query_rows_fast_kernel(const float *__restrict__ y, const float *__restrict__ po
   best.clear(sentinel);
   float tau = inf, max_v = -inf;
   u32 max_id = sentinel, corner_id = sentinel;
-  bool any_inf = false, tie = false, done = false;
+  bool any_inf = false, tie = false, done = false, dropped = false;
   int cnt = 0;
+
+  // ---- screen operands of the query (SCREEN only)
+  const int g8 = lane >> 2, t4 = lane & 3;
+  u32 qw[KS2][2];
+  float2 qn = make_float2(0.f, 0.f);
+  float scale2 = 0.f;
+  if (SCREEN) {
+    float scale = 1.0f;
+    {
+      const float cmax = __uint_as_float(*scr.scale_bits);
+      if (cmax > 0.f && cmax <= 3.0e38f) {
+        const int e = ilogbf(cmax);
+        scale = ldexpf(1.0f, 2 - max(-100, min(100, e)));               // the scale of the stored fp16 rows
+        if (e >= -30 && e <= 30) scale2 = scale * scale;               // outside: everything is measured
+      }
+    }
+    float ss = 0.f, n2 = 0.f;
+    const float *yr = y + x * (size_t)D;
+#pragma unroll
+    for (int v = 0; v < KS2; v++) {
+      constexpr int NC = D >= 32 ? 8 : 4;                             // coordinates of this lane's piece
+      const int c0 = D >= 32 ? 32 * v + 8 * t4 : 4 * t4;
+      u32 w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int i = 0; i < NC; i += 2) {
+        const float a = (yr[c0 + i] - scr.mean[c0 + i]) * scale, b = (yr[c0 + i + 1] - scr.mean[c0 + i + 1]) * scale;
+        const __half2 h = __floats2half2_rn(a, b);
+        const float ra = __low2float(h), rb = __high2float(h);
+        ss += a * a + b * b;
+        n2 += ra * ra + rb * rb;
+        w[i >> 1] = *reinterpret_cast<const u32 *>(&h);
+      }
+      qw[v][0] = (g8 & 1) ? w[1] : w[0];
+      qw[v][1] = D >= 32 ? ((g8 & 1) ? w[3] : w[2]) : 0u;
+    }
+    ss += __shfl_xor_sync(FULL, ss, 1); ss += __shfl_xor_sync(FULL, ss, 2);
+    n2 += __shfl_xor_sync(FULL, n2, 1); n2 += __shfl_xor_sync(FULL, n2, 2);
+    // the norm bound of screen_prep_kernel, with a little more slack for the different summation order
+    qn.x = SCREEN_SQRT_KAPPA * (sqrtf(ss) * (1.0f + 1.0f / 2048.0f) + sqrtf((float)D) * (1.0f / 16384.0f));
+    qn.y = n2;
+  }
 
   auto flush = [&]() {
     __syncwarp();
+    if (SCREEN && cnt > 0) {
+      const int c16 = (cnt + 15) & ~15;
+      if (lane < c16 - cnt) buf[cnt + lane] = buf[0];                   // pads: a valid row, dead by position
+      __syncwarp();
+      const float taus = scale2 > 0.f ? tau * scale2 : inf;
+      int V = 0;
+      for (int base = 0; base < c16; base += 16) {
+        const u32 c0 = buf[base + g8], c1 = buf[base + g8 + 8];
+        const unsigned short *p0 = scr.p16 + (size_t)c0 * D, *p1 = scr.p16 + (size_t)c1 * D;
+        float ca[4] = {0.f, 0.f, 0.f, 0.f}, cc[4] = {0.f, 0.f, 0.f, 0.f};
+        const u32 ce = (t4 & 1) ? c1 : c0;
+        const float2 cn = scr.nrm[ce];
+#pragma unroll
+        for (int v = 0; v < KS2; v++) {
+          uint4 ra, rc;
+          if (D >= 32) {
+            ra = *reinterpret_cast<const uint4 *>(p0 + 32 * v + 8 * t4);
+            rc = *reinterpret_cast<const uint4 *>(p1 + 32 * v + 8 * t4);
+          } else {
+            const uint2 w0 = *reinterpret_cast<const uint2 *>(p0 + 4 * t4), w1 = *reinterpret_cast<const uint2 *>(p1 + 4 * t4);
+            ra = make_uint4(w0.x, w0.y, 0u, 0u);
+            rc = make_uint4(w1.x, w1.y, 0u, 0u);
+          }
+          mma_f16_16816(ca, ra.x, ra.y, ra.z, ra.w, qw[v][0], qw[v][1]);
+          mma_f16_16816(cc, rc.x, rc.y, rc.z, rc.w, qw[v][0], qw[v][1]);
+        }
+        const float dot = (t4 & 1) ? cc[0] + cc[3] : ca[0] + ca[3];
+        const float t = qn.x + cn.x;
+        const float lo = __fmaf_rn(-t, t, __fmaf_rn(-2.0f, dot, qn.y + cn.y));
+        const bool pass = t4 < 2 && base + g8 + 8 * (t4 & 1) < cnt && lo <= taus;
+        const unsigned m = __ballot_sync(FULL, pass);
+        __syncwarp();                                                   // this round's ids are in registers everywhere
+        if (pass) buf[V + __popc(m & ((1u << lane) - 1))] = ce;
+        V += __popc(m);
+      }
+      if (V < cnt) dropped = true;
+      cnt = V;
+      __syncwarp();
+    }
     for (int base = 0; base < cnt; base += 2 * CPR) {
       u32 cid[2];
       float dist[2];
@@ -271,7 +370,7 @@ query_rows_fast_kernel(const float *__restrict__ y, const float *__restrict__ po
     u32 oi = __shfl_xor_sync(FULL, max_id, o);
     if (ov > max_v || (ov == max_v && oi < max_id)) { max_v = ov; max_id = oi; }
   }
-  if (q.prefix < q.len && !any_inf && corner_id == max_id) best.remove(corner_id, sentinel, lane);
+  if (q.prefix < q.len && !any_inf && !dropped && corner_id == max_id) best.remove(corner_id, sentinel, lane);
   if (lane < k) {
     list_ids[x * (size_t)k + lane] = best.id[0];
     list_dist[x * (size_t)k + lane] = best.v[0];
@@ -340,19 +439,34 @@ template <int E>
 static void launch_query_rows(int regs, size_t smem, annb_stream stream, const FT *y, const FT *points,
                               const QueryTables &q, const u32 *sign, size_t n, size_t ycnt, int d,
                               int d_short, int k, int ex, u32 *ids, FT *dist, const LiteralScratch &ls,
-                              int *status) {
+                              int *status, const annb_query_screen *screen) {
+  (void)screen;
   dim3 block(256), grid(grid_for(ycnt * 32, 256));
   bool fast = false;
 #ifdef USE_FLOAT
   {
     const char *off = getenv("ANN_B200_NO_FAST_QUERY");
     if (!(off && *off && *off != '0') && k <= 32 && (d == 16 || d == 32 || d == 64 || d == 128)) {
-      switch (d) {
-        case 16: query_rows_fast_kernel<16><<<grid, block, 0, stream>>>(y, points, q, sign, n, ycnt, d_short, k, ex, ids, dist, ls.list); break;
-        case 32: query_rows_fast_kernel<32><<<grid, block, 0, stream>>>(y, points, q, sign, n, ycnt, d_short, k, ex, ids, dist, ls.list); break;
-        case 64: query_rows_fast_kernel<64><<<grid, block, 0, stream>>>(y, points, q, sign, n, ycnt, d_short, k, ex, ids, dist, ls.list); break;
-        default: query_rows_fast_kernel<128><<<grid, block, 0, stream>>>(y, points, q, sign, n, ycnt, d_short, k, ex, ids, dist, ls.list); break;
+      QueryScreenDev sd = {NULL, NULL, NULL, NULL};
+      const char *soff = getenv("ANN_B200_QUERY_SCREEN");
+      const bool use_screen = screen && screen->points16 && screen->nrm && screen->mean && screen->scale_bits &&
+                              !(soff && *soff == '0');
+      if (use_screen) {
+        sd.p16 = (const unsigned short *)screen->points16;
+        sd.nrm = (const float2 *)screen->nrm;
+        sd.mean = (const float *)screen->mean;
+        sd.scale_bits = screen->scale_bits;
       }
+#define QF_CASE(DD)                                                                                              \
+  if (use_screen) query_rows_fast_kernel<DD, true><<<grid, block, 0, stream>>>(y, points, q, sign, n, ycnt, d_short, k, ex, ids, dist, ls.list, sd); \
+  else query_rows_fast_kernel<DD, false><<<grid, block, 0, stream>>>(y, points, q, sign, n, ycnt, d_short, k, ex, ids, dist, ls.list, sd);
+      switch (d) {
+        case 16: QF_CASE(16) break;
+        case 32: QF_CASE(32) break;
+        case 64: QF_CASE(64) break;
+        default: QF_CASE(128) break;
+      }
+#undef QF_CASE
       fast = true;
     }
   }
@@ -378,11 +492,20 @@ static void launch_query_rows(int regs, size_t smem, annb_stream stream, const F
   LAUNCH_CHECK("query_literal");
 }
 
+extern "C" int annb_query_screen_applies(size_t d, size_t k) {
+#ifdef USE_FLOAT
+  return (d == 16 || d == 32 || d == 64 || d == 128) && k <= 32;
+#else
+  (void)d; (void)k;
+  return 0;
+#endif
+}
+
 extern "C" void annb_query_rows(const FT *y, const FT *points, const u32 *const *tables,
                                 const size_t *par_maxes, int tries, const u32 *sign, size_t n,
                                 size_t ycnt, size_t d, size_t d_short, size_t k, int exclude_self,
                                 u32 *list_ids, FT *list_dist, void *scratch, size_t scratch_bytes,
-                                int *status, annb_stream stream) {
+                                int *status, const annb_query_screen *screen, annb_stream stream) {
   int regs = list_regs(k);
   if (!regs) fatal_config("k > 256");
   if (tries > 64) fatal_config("more than 64 tries in a saved index");
@@ -410,7 +533,7 @@ extern "C" void annb_query_rows(const FT *y, const FT *points, const u32 *const 
   if (smem > 200 * 1024) fatal_config("d too large for the generic distance path");
   LiteralScratch ls = carve_literal_scratch(scratch, scratch_bytes, ycnt);
   RT_CHECK(cudaMemsetAsync(ls.list.count, 0, sizeof(u32), stream));
-#define Q_ARGS regs, smem, stream, y, points, q, sign, n, ycnt, (int)d, (int)d_short, (int)k, exclude_self, list_ids, list_dist, ls, status
+#define Q_ARGS regs, smem, stream, y, points, q, sign, n, ycnt, (int)d, (int)d_short, (int)k, exclude_self, list_ids, list_dist, ls, status, screen
   switch (mode) {
     case 0: launch_query_rows<0>(Q_ARGS); break;
     case 1: launch_query_rows<1>(Q_ARGS); break;

@@ -212,11 +212,23 @@ void annb_supercharge_screen_stats(unsigned long long out[2], int reset);
  * annb_narrow_ids: size_t -> 32-bit ids on the device (host-format tables / graph).        */
 void annb_query_hash(const ftype *y, const ftype *mean, const ftype *bases, size_t ycnt, size_t d,
                      size_t d_short, int tries, annb_u32 *sign, annb_stream stream);
+/* screen (may be NULL; float, d in {16,32,64,128}, k <= 32): the fp16 copy of the indexed points
+ * with its (norm bound, squared norm) pairs and scale word (annb_screen_scale +
+ * annb_screen_prep_points) and the column means; candidates are then bracketed against the
+ * running k-th best and only the survivors are measured exactly — same lists, bit for bit
+ * (ANN_B200_QUERY_SCREEN=0 switches it off)                                                  */
+typedef struct {
+  const void *points16;
+  const void *nrm;
+  const ftype *mean;
+  const unsigned *scale_bits;
+} annb_query_screen;
+int annb_query_screen_applies(size_t d, size_t k);
 void annb_query_rows(const ftype *y, const ftype *points, const annb_u32 *const *tables,
                      const size_t *par_maxes, int tries, const annb_u32 *sign, size_t n,
                      size_t ycnt, size_t d, size_t d_short, size_t k, int exclude_self,
                      annb_u32 *list_ids, ftype *list_dist, void *scratch, size_t scratch_bytes,
-                     int *status, annb_stream stream);
+                     int *status, const annb_query_screen *screen, annb_stream stream);
 void annb_narrow_ids(const size_t *src, size_t count, annb_u32 *dst, annb_stream stream);
 
 /* (point, real candidate) pairs whose distance S3 evaluated since the last reset (synchronous);

@@ -78,23 +78,41 @@ def test_query_cache_is_dropped_with_the_save(gpu):
 
 @pytest.mark.parametrize("n,d,k,tries,ycnt", [(20000, 64, 16, 8, 5000), (9000, 32, 10, 10, 3000), (6000, 16, 32, 3, 1000)])
 def test_pipelined_query_rows_equal_the_generic_kernel(gpu, n, d, k, tries, ycnt):
-    """query_rows_fast_kernel (buffered ids, whole-line loads) vs the warp-per-row kernel it
-    replaces: every bit of ids and distances, with and without self-exclusion."""
+    """query_rows_fast_kernel (buffered ids, whole-line loads), with and without its fp16 screen,
+    vs the warp-per-row kernel it replaces: every bit of ids and distances, with and without
+    self-exclusion, on Gaussian and on offset/clustered data."""
     import os
     b = gpu[np.dtype(np.float32)]
     rng = np.random.default_rng(n + d)
     pts = rng.standard_normal((n, d)).astype(np.float32)
     y = rng.standard_normal((ycnt, d)).astype(np.float32)
     r = b.precomp(pts, k, tries, want_save=True, seed=9)
-    fast, fast_s = b.query(r.save, pts, y), b.query(r.save, pts, pts)
+    fast, fast_s = b.query(r.save, pts, y), b.query(r.save, pts, pts)          # screened (default)
+    os.environ["ANN_B200_QUERY_SCREEN"] = "0"
+    try:
+        plain, plain_s = b.query(r.save, pts, y), b.query(r.save, pts, pts)    # pipelined, every candidate exact
+    finally:
+        del os.environ["ANN_B200_QUERY_SCREEN"]
     os.environ["ANN_B200_NO_FAST_QUERY"] = "1"
     try:
-        slow, slow_s = b.query(r.save, pts, y), b.query(r.save, pts, pts)
+        slow, slow_s = b.query(r.save, pts, y), b.query(r.save, pts, pts)      # warp-per-row kernel of round 1
     finally:
         del os.environ["ANN_B200_NO_FAST_QUERY"]
-    for a, c in ((fast, slow), (fast_s, slow_s)):
+    for a, c in ((fast, slow), (fast_s, slow_s), (plain, slow), (plain_s, slow_s)):
         assert np.array_equal(a.ids, c.ids) and same_bits(a.dists, c.dists)
-    r.save.free()
+    # data that stresses the brackets: a common offset and tight clusters
+    centres = rng.standard_normal((40, d)) * 30.0 + 500.0
+    pts2 = (centres[rng.integers(0, 40, n)] + rng.standard_normal((n, d)) * 0.01).astype(np.float32)
+    y2 = (centres[rng.integers(0, 40, ycnt)] + rng.standard_normal((ycnt, d)) * 0.01).astype(np.float32)
+    r2 = b.precomp(pts2, k, tries, want_save=True, seed=10)
+    a = b.query(r2.save, pts2, y2)
+    os.environ["ANN_B200_NO_FAST_QUERY"] = "1"
+    try:
+        c = b.query(r2.save, pts2, y2)
+    finally:
+        del os.environ["ANN_B200_NO_FAST_QUERY"]
+    assert np.array_equal(a.ids, c.ids) and same_bits(a.dists, c.dists)
+    r.save.free(); r2.save.free()
 
 
 def test_corrected_sign_layout_is_opt_in_and_finds_the_point_itself(gpu):
