@@ -58,8 +58,68 @@ query_hash_kernel(const FT *__restrict__ y, const FT *__restrict__ mean, const F
   if (lane == 0) sign[w] = h;
 }
 
+// d in {16, 32, 64, 128, 256}: one warp per query for ALL tries, the centred query in registers
+// (lane l holds coordinates l + 32 s), the basis vectors through the L1 (T*d_short*d values,
+// 32 KB at cfg3), the product tree of the reference as lane-local levels followed by
+// xor-shuffles.  Every level is m[z] = m[z] + (m[z + h] + 0) as above; a + (b + 0) gives the
+// same bits on both partners of a shuffle (IEEE addition commutes, signed zeros included), so
+// the lanes that hold the live half of a level hold exactly the reference's values.
+template <int E>
+__global__ void __launch_bounds__(256)
+query_hash_warp_kernel(const FT *__restrict__ y, const FT *__restrict__ mean, const FT *__restrict__ bases,
+                       size_t ycnt, int d, int d_short, int tries, u32 *__restrict__ sign) {
+  const int lane = threadIdx.x & 31;
+  const size_t x = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (x >= ycnt) return;
+  FT c[E];
+#pragma unroll
+  for (int s = 0; s < E; s++) {
+    const int z = lane + 32 * s;
+    c[s] = z < d ? y[x * (size_t)d + z] - mean[z] : (FT)0;
+  }
+  for (int t = 0; t < tries; t++) {
+    u32 h = 0;
+    for (int i = 0; i < d_short; i++) {
+      const FT *b = bases + ((size_t)t * d_short + i) * d;
+      FT m[E];
+#pragma unroll
+      for (int s = 0; s < E; s++) {
+        const int z = lane + 32 * s;
+        m[s] = z < d ? c[s] * b[z] : (FT)0;
+      }
+#pragma unroll
+      for (int hh = E / 2; hh >= 1; hh >>= 1)
+#pragma unroll
+        for (int s = 0; s < hh; s++) m[s] = m[s] + (m[s + hh] + (FT)0);
+      FT v = m[0];
+      if (d >= 32) v = v + (__shfl_xor_sync(FULL, v, 16) + (FT)0);
+      v = v + (__shfl_xor_sync(FULL, v, 8) + (FT)0);
+      v = v + (__shfl_xor_sync(FULL, v, 4) + (FT)0);
+      v = v + (__shfl_xor_sync(FULL, v, 2) + (FT)0);
+      v = v + (__shfl_xor_sync(FULL, v, 1) + (FT)0);
+      h = (h << 1) | sign_bit(v);                      // lane 0 holds the reference's sum
+    }
+    if (lane == 0) sign[x * (size_t)tries + t] = h;
+  }
+}
+
 extern "C" void annb_query_hash(const FT *y, const FT *mean, const FT *bases, size_t ycnt, size_t d,
                                 size_t d_short, int tries, u32 *sign, annb_stream stream) {
+  {
+    const char *off = getenv("ANN_B200_NO_FAST_QUERY");
+    const int E = row_mode(d);                         // 0 = generic, else d/32 (d = 16 -> 1)
+    if (E && !(off && *off && *off != '0')) {
+      dim3 block(256), grid(grid_for(ycnt * 32, 256));
+      switch (E) {
+        case 1: query_hash_warp_kernel<1><<<grid, block, 0, stream>>>(y, mean, bases, ycnt, (int)d, (int)d_short, tries, sign); break;
+        case 2: query_hash_warp_kernel<2><<<grid, block, 0, stream>>>(y, mean, bases, ycnt, (int)d, (int)d_short, tries, sign); break;
+        case 4: query_hash_warp_kernel<4><<<grid, block, 0, stream>>>(y, mean, bases, ycnt, (int)d, (int)d_short, tries, sign); break;
+        default: query_hash_warp_kernel<8><<<grid, block, 0, stream>>>(y, mean, bases, ycnt, (int)d, (int)d_short, tries, sign); break;
+      }
+      LAUNCH_CHECK("query_hash_warp");
+      return;
+    }
+  }
   size_t smem = 8 * d * sizeof(FT);
   if (smem > 200 * 1024) fatal_config("d too large for the query projection");
   if (smem > 48 * 1024)
@@ -189,6 +249,7 @@ query_rows_fast_kernel(const float *__restrict__ y, const float *__restrict__ po
   constexpr int LPC = D / 8, CPR = 32 / LPC;
   constexpr int KS2 = D >= 32 ? D / 32 : 1;
   __shared__ __align__(16) u32 s_buf[8][QBUF + 16];
+  __shared__ u32 s_seg[8][29][32];                       // first 32 ids of the d_short+1 <= 29 table rows of a try
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   size_t x = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (x >= ycnt) return;
@@ -254,33 +315,45 @@ query_rows_fast_kernel(const float *__restrict__ y, const float *__restrict__ po
       __syncwarp();
       const float taus = scale2 > 0.f ? tau * scale2 : inf;
       int V = 0;
-      for (int base = 0; base < c16; base += 16) {
+      // a round's rows are requested while the previous round is evaluated
+      uint4 ra[KS2], rc[KS2];
+      u32 ce = 0;
+      float2 cn = make_float2(0.f, 0.f);
+      auto load = [&](int base) {
         const u32 c0 = buf[base + g8], c1 = buf[base + g8 + 8];
         const unsigned short *p0 = scr.p16 + (size_t)c0 * D, *p1 = scr.p16 + (size_t)c1 * D;
-        float ca[4] = {0.f, 0.f, 0.f, 0.f}, cc[4] = {0.f, 0.f, 0.f, 0.f};
-        const u32 ce = (t4 & 1) ? c1 : c0;
-        const float2 cn = scr.nrm[ce];
 #pragma unroll
         for (int v = 0; v < KS2; v++) {
-          uint4 ra, rc;
           if (D >= 32) {
-            ra = *reinterpret_cast<const uint4 *>(p0 + 32 * v + 8 * t4);
-            rc = *reinterpret_cast<const uint4 *>(p1 + 32 * v + 8 * t4);
+            ra[v] = *reinterpret_cast<const uint4 *>(p0 + 32 * v + 8 * t4);
+            rc[v] = *reinterpret_cast<const uint4 *>(p1 + 32 * v + 8 * t4);
           } else {
             const uint2 w0 = *reinterpret_cast<const uint2 *>(p0 + 4 * t4), w1 = *reinterpret_cast<const uint2 *>(p1 + 4 * t4);
-            ra = make_uint4(w0.x, w0.y, 0u, 0u);
-            rc = make_uint4(w1.x, w1.y, 0u, 0u);
+            ra[v] = make_uint4(w0.x, w0.y, 0u, 0u);
+            rc[v] = make_uint4(w1.x, w1.y, 0u, 0u);
           }
-          mma_f16_16816(ca, ra.x, ra.y, ra.z, ra.w, qw[v][0], qw[v][1]);
-          mma_f16_16816(cc, rc.x, rc.y, rc.z, rc.w, qw[v][0], qw[v][1]);
         }
+        ce = (t4 & 1) ? c1 : c0;
+        cn = scr.nrm[ce];
+      };
+      load(0);
+      for (int base = 0; base < c16; base += 16) {
+        float ca[4] = {0.f, 0.f, 0.f, 0.f}, cc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int v = 0; v < KS2; v++) {
+          mma_f16_16816(ca, ra[v].x, ra[v].y, ra[v].z, ra[v].w, qw[v][0], qw[v][1]);
+          mma_f16_16816(cc, rc[v].x, rc[v].y, rc[v].z, rc[v].w, qw[v][0], qw[v][1]);
+        }
+        const u32 cur = ce;
+        const float2 cnn = cn;
+        if (base + 16 < c16) load(base + 16);               // ids of the next round are read before this round's survivors are written
         const float dot = (t4 & 1) ? cc[0] + cc[3] : ca[0] + ca[3];
-        const float t = qn.x + cn.x;
-        const float lo = __fmaf_rn(-t, t, __fmaf_rn(-2.0f, dot, qn.y + cn.y));
+        const float t = qn.x + cnn.x;
+        const float lo = __fmaf_rn(-t, t, __fmaf_rn(-2.0f, dot, qn.y + cnn.y));
         const bool pass = t4 < 2 && base + g8 + 8 * (t4 & 1) < cnt && lo <= taus;
         const unsigned m = __ballot_sync(FULL, pass);
-        __syncwarp();                                                   // this round's ids are in registers everywhere
-        if (pass) buf[V + __popc(m & ((1u << lane) - 1))] = ce;
+        __syncwarp();
+        if (pass) buf[V + __popc(m & ((1u << lane) - 1))] = cur;
         V += __popc(m);
       }
       if (V < cnt) dropped = true;
@@ -335,20 +408,40 @@ query_rows_fast_kernel(const float *__restrict__ y, const float *__restrict__ po
   for (int t = 0; t < q.tries && !done; t++) {
     const u32 h = sign[(size_t)t * q.s_try + x * q.s_row];
     const u32 w = q.width[t];
+    // The first 32 ids of ALL d_short+1 table rows of the try are requested before any of them
+    // is consumed and parked in shared memory: one dependent L2 round trip per segment (136 per
+    // query at cfg3) was most of this kernel's time.  (Real ids are a prefix of a table row, so
+    // only buckets with more than 32 points need a second, dependent load.)
+    u32 (*seg)[32] = s_seg[wib];
+    {
+      u32 v[8];
+      for (int f0 = 0; f0 <= d_short; f0 += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int f = f0 + j;
+          v[j] = sentinel;
+          if (f <= d_short && (u32)lane < w) v[j] = q.tab[t][(size_t)(h ^ (f ? (1u << (f - 1)) : 0u)) * w + lane];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          if (f0 + j <= d_short) seg[f0 + j][lane] = v[j];
+      }
+    }
+    __syncwarp();
     for (int f = 0; f <= d_short; f++) {
       unsigned long long col = (unsigned long long)(d_short + 1) * q.offset[t] + (unsigned long long)f * w;
       const u32 *row = q.tab[t] + (size_t)(h ^ (f ? (1u << (f - 1)) : 0u)) * w;
       if (col >= q.prefix) {
-        if (col == q.prefix && w) corner_id = row[0];
+        if (col == q.prefix && w) corner_id = seg[f][0];
         done = true;
         break;
       }
       unsigned long long room = q.prefix - col;
       u32 take = w < room ? w : (u32)room;
-      if (take < w) { corner_id = row[take]; done = true; }
+      if (take < w) { corner_id = take < 32 ? seg[f][take] : row[take]; done = true; }
       for (u32 z0 = 0; z0 < take; z0 += 32) {
         const u32 z = z0 + lane;
-        const u32 id = z < take ? row[z] : sentinel;
+        const u32 id = z < take ? (z0 == 0 ? seg[f][lane] : row[z]) : sentinel;
         // pads fill the tail of a table row, so the real ids are a prefix of it
         const unsigned real = __ballot_sync(FULL, z < take && id < sentinel);
         if (__ballot_sync(FULL, z < take && id >= sentinel)) any_inf = true;
@@ -362,6 +455,7 @@ query_rows_fast_kernel(const float *__restrict__ y, const float *__restrict__ po
       }
       if (done) break;
     }
+    __syncwarp();
   }
   flush();
 #pragma unroll
