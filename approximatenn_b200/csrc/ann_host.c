@@ -498,6 +498,10 @@ size_t *annh_precomp_impl(size_t n, size_t k, size_t d, const ftype *points, int
              (full_result ? pad256(np * k * 4) + pad256(np * k * w) : 0);
   else
     fixed += pad256(n * k * 4) * 3 + pad256(n * k * w) * 3;
+  /* cutoff carried from try to try (annb200.h): only where the merged row is sorted as a whole,
+   * i.e. k*tries is a power of two (no prefix cut, no corner rule), and every list is merged at once */
+  int use_cut = Tl >= 2 && k * T >= 16 && ((k * T) & (k * T - 1)) == 0 && annb_cutoff_applies(d, d_short, k);
+  if (use_cut) fixed += pad256(n * k * w) + pad256(n * w);
   size_t group = Tl ? Tl : 1;                                  /* lists kept before a merge */
   if (!sharded && fixed + group * list_bytes + 512 > G.arena_bytes) {
     /* the arena has to grow: see what the device can give (cudaMemGetInfo costs milliseconds,
@@ -527,6 +531,7 @@ size_t *annh_precomp_impl(size_t n, size_t k, size_t d, const ftype *points, int
       warned = 1;
     }
   }
+  if (group < Tl) use_cut = 0;
   annh_arena_reserve(fixed + group * list_bytes + 512);
 
   ftype *dX = annh_arena_take(np * d * w), *dXs = annh_arena_take(n * d * w), *dmean = annh_arena_take(d * w);
@@ -559,6 +564,8 @@ size_t *annh_precomp_impl(size_t n, size_t k, size_t d, const ftype *points, int
   void *dN16 = s5_screened ? annh_arena_take(n * 8) : NULL;
   void *dlocal = s5_local ? annh_arena_take(local_bytes) : NULL;
   annb_u32 *dperm = s5_local ? annh_arena_take(my_rows * 4) : NULL;
+  ftype *drun = use_cut ? annh_arena_take(n * k * w) : NULL;    /* k smallest distinct distances so far */
+  ftype *dcut = use_cut ? annh_arena_take(n * w) : NULL;        /* their largest: the cutoff of a point  */
   annb_u32 *dhash_all = (sharded && save) ? annh_arena_take(T * n * 4) : NULL;
   annb_u32 *ds_ids = sharded ? annh_arena_take(T * my_rows * k * 4) : NULL;   /* [T][my_rows][k] */
   ftype *ds_dist = sharded ? annh_arena_take(T * my_rows * k * w) : NULL;
@@ -660,8 +667,10 @@ size_t *annh_precomp_impl(size_t n, size_t k, size_t d, const ftype *points, int
       else annb_gather_rows(dX, dorder, n, d, dXs, st);
       span_end(sp);
       sp = span_begin(4);
-      annb_leaf_topk(dXs, dmean, dorder, doffset, hash_t, dtmax + t, n, d, d_short, k, dl_ids + j * n * k,
-                     dl_dist + j * n * k, dscratch, dstatus, screened ? dscreen : NULL, screened, st);
+      annb_leaf_topk_cut(dXs, dmean, dorder, doffset, hash_t, dtmax + t, n, d, d_short, k, dl_ids + j * n * k,
+                         dl_dist + j * n * k, dscratch, dstatus, screened ? dscreen : NULL, screened,
+                         (use_cut && j > 0) ? dcut : NULL, st);
+      if (use_cut && j + 1 < Tl) annb_cutoff_update(dl_dist + j * n * k, drun, dcut, n, k, j == 0, st);
       span_end(sp);
       admit[j] = annb200_dist_admit(k, tries, (int)t);
     }

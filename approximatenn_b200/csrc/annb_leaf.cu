@@ -766,7 +766,7 @@ static void launch_screen(annb_stream stream, const FT *sp, const FT *mean, void
                           const unsigned *scale_bits, int rows_prepared,
                           const u32 *order, const u32 *offset, const u32 *tmax, size_t n,
                           size_t buckets, int d_short, int k, u32 *ids, FT *dist, TieList flags,
-                          ScreenOverflow *ovf_out) {
+                          ScreenOverflow *ovf_out, const FT *cutoff) {
   ScreenArea a = screen_area(scratch, n, D);
   unsigned short *sp16 = a.sp16;
   float2 *nrm = a.nrm;
@@ -777,6 +777,7 @@ static void launch_screen(annb_stream stream, const FT *sp, const FT *mean, void
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cutoff && !(rows_prepared && scale_bits)) fatal_config("a leaf cutoff needs the prepared rows and their scale word");
   if (!rows_prepared) {
     if (!scale_bits) {
       launch_maxabs(stream, sp, mean, n, D, a.words);
@@ -803,7 +804,7 @@ static void launch_screen(annb_stream stream, const FT *sp, const FT *mean, void
   if (grid > resident) grid = resident;
   u32 *ticket = flags.count + 32;
   RT_CHECK(cudaMemsetAsync(ticket, 0, sizeof(u32), stream));
-  leaf_screen_kernel<D><<<grid, 32, smem, stream>>>(sp, sp16, nrm, order, offset, tmax, n, buckets, d_short, k, ids, dist, flags, 0x8000000080000000ull, ticket, ct, ovf);
+  leaf_screen_kernel<D><<<grid, 32, smem, stream>>>(sp, sp16, nrm, order, offset, tmax, n, buckets, d_short, k, ids, dist, flags, 0x8000000080000000ull, ticket, ct, ovf, cutoff, scale_bits);
   LAUNCH_CHECK("leaf_screen");
   *ovf_out = ovf;
 }
@@ -813,10 +814,10 @@ static bool try_launch_screen(annb_stream stream, const FT *sp, const FT *mean, 
                               const unsigned *scale_bits, int rows_prepared,
                               const u32 *order, const u32 *offset, const u32 *tmax, size_t n,
                               size_t buckets, size_t d, int d_short, size_t k, u32 *ids, FT *dist,
-                              TieList flags) {
+                              TieList flags, const FT *cutoff) {
   if (!screen_enabled() || !screen_covers(d, (size_t)d_short, k)) return false;
   ScreenOverflow ovf;
-#define SCR_ARGS stream, sp, mean, scratch, scale_bits, rows_prepared, order, offset, tmax, n, buckets, d_short, (int)k, ids, dist, flags, &ovf
+#define SCR_ARGS stream, sp, mean, scratch, scale_bits, rows_prepared, order, offset, tmax, n, buckets, d_short, (int)k, ids, dist, flags, &ovf, cutoff
   if (d == 16) launch_screen<16>(SCR_ARGS);
   else if (d == 32) launch_screen<32>(SCR_ARGS);
   else launch_screen<64>(SCR_ARGS);
@@ -828,11 +829,144 @@ static bool try_launch_screen(annb_stream stream, const FT *sp, const FT *mean, 
 }
 #endif
 
+// =====================================================================================
+// cutoff carried from try to try
+// =====================================================================================
+// The merge keeps the k smallest distinct ids of a point over all tries, so an entry of a later
+// try that is farther than the k-th best found so far can never be reported.  `run` holds, per
+// point, the k smallest DISTINCT distance values seen in the lists so far (equal ids carry equal
+// distances, so k distinct values belong to at least k distinct ids and their largest bounds the
+// final k-th distance from above; counting values instead of ids keeps the ids out of this
+// pass and only loosens the bound in rows with exact ties).  cutoff[x] = that value, +inf while
+// fewer than k are known.  One thread per point, everything in registers: duplicates of the new
+// list against the running one are turned into +inf, the new list is re-sorted by a bitonic
+// network and the two ascending lists are merged by the usual reverse / min / bitonic-merge.
+#define CUT_CE(a, b) { const FT lo_ = (a) < (b) ? (a) : (b), hi_ = (a) < (b) ? (b) : (a); (a) = lo_; (b) = hi_; }
+template <int K>
+__global__ void __launch_bounds__(128)
+cutoff_update_kernel(const FT *__restrict__ new_dist, FT *__restrict__ run, FT *__restrict__ cutoff,
+                     size_t n, int k, int first) {
+  const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n) return;
+  const FT inf = ft_inf();
+  FT v[K], r[K];
+  constexpr int VW = 16 / sizeof(FT);
+  if (k == K) {
+#pragma unroll
+    for (int i = 0; i < K / VW; i++) {
+      FT tmp[VW];
+      *reinterpret_cast<uint4 *>(tmp) = reinterpret_cast<const uint4 *>(new_dist + x * (size_t)K)[i];
+#pragma unroll
+      for (int e = 0; e < VW; e++) v[i * VW + e] = tmp[e];
+      if (!first) *reinterpret_cast<uint4 *>(tmp) = reinterpret_cast<const uint4 *>(run + x * (size_t)K)[i];
+#pragma unroll
+      for (int e = 0; e < VW; e++) r[i * VW + e] = first ? inf : tmp[e];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+      v[i] = i < k ? new_dist[x * (size_t)k + i] : inf;
+      r[i] = (i < k && !first) ? run[x * (size_t)k + i] : inf;
+    }
+  }
+  bool bad = false;                                   // NaN anywhere: no cutoff for this point
+#pragma unroll
+  for (int i = 0; i < K; i++) bad |= (v[i] != v[i]) || (r[i] != r[i]);
+  // distinct values only: repeats inside the (ascending) new list, then repeats of the running list
+  bool dup[K];
+  dup[0] = false;
+#pragma unroll
+  for (int j = 1; j < K; j++) dup[j] = v[j] == v[j - 1];
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+#pragma unroll
+    for (int i = 0; i < K; i++) dup[j] |= v[j] == r[i];
+  }
+#pragma unroll
+  for (int j = 0; j < K; j++) if (dup[j]) v[j] = inf;
+  // ascending sort of v (bitonic network, compile-time indices)
+#pragma unroll
+  for (int size = 2; size <= K; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+#pragma unroll
+      for (int i = 0; i < K; i++) {
+        const int p = i ^ stride;
+        if (p > i) {
+          if ((i & size) == 0) CUT_CE(v[i], v[p]) else CUT_CE(v[p], v[i])
+        }
+      }
+    }
+  }
+  // the K smallest of the two ascending lists: min against the reversed list is bitonic
+#pragma unroll
+  for (int i = 0; i < K; i++) r[i] = r[i] < v[K - 1 - i] ? r[i] : v[K - 1 - i];
+#pragma unroll
+  for (int stride = K >> 1; stride >= 1; stride >>= 1) {
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+      const int p = i ^ stride;
+      if (p > i) CUT_CE(r[i], r[p])
+    }
+  }
+  if (bad) {
+#pragma unroll
+    for (int i = 0; i < K; i++) r[i] = inf;
+  }
+  FT kth = inf;
+#pragma unroll
+  for (int i = 0; i < K; i++) if (i == k - 1) kth = r[i];
+  cutoff[x] = kth;
+  if (k == K) {
+#pragma unroll
+    for (int i = 0; i < K / VW; i++) {
+      FT tmp[VW];
+#pragma unroll
+      for (int e = 0; e < VW; e++) tmp[e] = r[i * VW + e];
+      reinterpret_cast<uint4 *>(run + x * (size_t)K)[i] = *reinterpret_cast<uint4 *>(tmp);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < K; i++) if (i < k) run[x * (size_t)k + i] = r[i];
+  }
+}
+#undef CUT_CE
+
+// 1 (default): later tries of the screened path stop their lists at the running cutoff; 0: full
+// lists.  The merged result is the same either way (tests compare).  ANN_B200_CUTOFF=0 switches it off.
+static int cutoff_mode = -1;
+extern "C" void annb_leaf_cutoff_mode(int on) { cutoff_mode = on ? 1 : 0; }
+extern "C" int annb_cutoff_applies(size_t d, size_t d_short, size_t k) {
+  if (cutoff_mode < 0) {
+    const char *e = getenv("ANN_B200_CUTOFF");
+    cutoff_mode = (e && *e) ? (*e != '0') : 1;
+  }
+  return cutoff_mode && k <= 16 && annb_screen_applies(d, d_short, k);
+}
+extern "C" void annb_cutoff_update(const FT *new_dist, FT *run, FT *cutoff, size_t n, size_t k, int first,
+                                   annb_stream stream) {
+  if (k < 1 || k > 16) fatal_config("annb_cutoff_update: k must be 1..16");
+  cutoff_update_kernel<16><<<grid_for(n, 128), 128, 0, stream>>>(new_dist, run, cutoff, n, (int)k, first);
+  LAUNCH_CHECK("cutoff_update");
+}
+
 extern "C" void annb_leaf_topk(const FT *sorted_points, const FT *mean, const u32 *order,
                                const u32 *offset, const u32 *hash, const u32 *tmax, size_t n,
                                size_t d, size_t d_short, size_t k, u32 *list_ids, FT *list_dist,
                                void *scratch, int *status, const unsigned *scale_bits,
                                int rows_prepared, annb_stream stream) {
+  annb_leaf_topk_cut(sorted_points, mean, order, offset, hash, tmax, n, d, d_short, k, list_ids, list_dist, scratch,
+                     status, scale_bits, rows_prepared, NULL, stream);
+}
+
+// With `cutoff` (per point an upper bound of its final k-th distance, annb_cutoff_update) a list
+// may stop early: every candidate at or below the cutoff is there, at the position it has in the
+// full list, and whatever else the full list holds may be replaced by (n, +inf).
+extern "C" void annb_leaf_topk_cut(const FT *sorted_points, const FT *mean, const u32 *order,
+                                   const u32 *offset, const u32 *hash, const u32 *tmax, size_t n,
+                                   size_t d, size_t d_short, size_t k, u32 *list_ids, FT *list_dist,
+                                   void *scratch, int *status, const unsigned *scale_bits,
+                                   int rows_prepared, const FT *cutoff, annb_stream stream) {
   int regs = list_regs(k);
   if (!regs) fatal_config("k > 256");
   // scratch layout: rank_of[n] | tie list (count, rows[n]) | literal-row slabs
@@ -852,7 +986,9 @@ extern "C" void annb_leaf_topk(const FT *sorted_points, const FT *mean, const u3
   bool done = false;
 #ifdef USE_FLOAT
   done = try_launch_screen(stream, sorted_points, mean, scratch, scale_bits, rows_prepared, order, offset, tmax,
-                           n, buckets, d, (int)d_short, k, list_ids, list_dist, flags);
+                           n, buckets, d, (int)d_short, k, list_ids, list_dist, flags, cutoff);
+#else
+  (void)cutoff;
 #endif
   if (!done && !try_launch_tile(stream, sorted_points, order, offset, tmax, n, buckets, d, (int)d_short, k,
                                 list_ids, list_dist, flags)) {

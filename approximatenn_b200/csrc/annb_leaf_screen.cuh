@@ -239,7 +239,8 @@ leaf_screen_kernel(const float *__restrict__ sp, const unsigned short *__restric
                    const u32 *__restrict__ offset, const u32 *__restrict__ tmax_p, size_t n,
                    size_t buckets, int d_short, int k, u32 *__restrict__ list_ids,
                    float *__restrict__ list_dist, TieList ties, unsigned long long negzero2,
-                   u32 *__restrict__ ticket, int CT, ScreenOverflow ovf) {
+                   u32 *__restrict__ ticket, int CT, ScreenOverflow ovf,
+                   const float *__restrict__ cutoff, const unsigned *__restrict__ scale_bits) {
   constexpr int KS = D / 16;                                           // k-steps per candidate tile
   constexpr int NV = D / 16;                                           // 16-byte pieces per lane in the exact tree
   constexpr int QROW = ScreenOverlay<D>::QROW;
@@ -261,6 +262,14 @@ leaf_screen_kernel(const float *__restrict__ sp, const unsigned short *__restric
   unsigned short *slist = reinterpret_cast<unsigned short *>(segrow + 32);    // [32][SCREEN_HALF] candidate index
   const u32 sentinel = (u32)n;
   const float inf = ft_inf();
+  // cutoff (optional): per point an upper bound of its FINAL k-th distance, known from earlier
+  // tries (cutoff_update_kernel).  In the units of the brackets it is cutoff * scale^2; outside
+  // the trusted range of the scale it is ignored.
+  double cut_scale2 = 0.0;
+  if (cutoff) {
+    const float sc = screen_scale(*scale_bits);
+    if (sc >= 1.0f / 268435456.0f && sc <= 4294967296.0f) cut_scale2 = (double)sc * (double)sc;
+  }
 
   for (;;) {
     size_t b = 0;
@@ -318,6 +327,12 @@ leaf_screen_kernel(const float *__restrict__ sp, const unsigned short *__restric
 
     for (u32 qbase = 0; qbase < Q && !overflow; qbase += 16) {
       const u32 Qp = min(16u, Q - qbase);
+      // the cutoff of query (lane & 15), requested now and used by the scan
+      float cut_s = inf;
+      if (cut_scale2 != 0.0 && (u32)(lane & 15) < Qp) {
+        const float c = cutoff[order[(size_t)beg + qbase + (lane & 15)]];
+        cut_s = __double2float_ru((double)c * cut_scale2);          // exact product, rounded up
+      }
       // ---- pass 1: bounds for query rows g and g + 8 of this tile ----------------------
       {
         const bool qv0 = (u32)g < Qp, qv1 = (u32)g + 8 < Qp;
@@ -417,7 +432,10 @@ leaf_screen_kernel(const float *__restrict__ sp, const unsigned short *__restric
         const u32 half_cols = C16 >> 1;                                 // multiple of 8
         // thresholds as fp16 rounded up; +inf (fewer than 16 candidates) becomes the largest
         // finite value so that the +inf of pads and of the query itself never passes
-        const float thf = theta[sq];
+        // a candidate with D <= cutoff has lo <= D <= cut_s, so it passes; what is dropped beyond
+        // Theta could not enter this try's k best, what is dropped beyond the cutoff is farther
+        // than the point's final k-th neighbour and could not survive the merge (fminf ignores NaN)
+        const float thf = fminf(theta[sq], cut_s);
         __half thh = __float2half_ru(thf);
         if (__hisinf(thh)) thh = __ushort_as_half((unsigned short)0x7bff);
         const __half2 th2 = __half2half2(thh);

@@ -118,6 +118,25 @@ void annb_leaf_topk(const ftype *sorted_points, const ftype *mean, const annb_u3
                     void *scratch, int *status, const unsigned *scale_bits, int rows_prepared,
                     annb_stream stream);
 
+/* Cutoff carried from try to try (screened path only).  The merge of the per-try lists keeps the
+ * k smallest distinct ids, so an entry farther than the k-th best already found can never be
+ * reported: with `cutoff` (one value per point, original order) a later try's list holds every
+ * candidate at or below cutoff[x] at its position in the full list and may hold (n, +inf)
+ * beyond.  annb_cutoff_update folds a finished list into the running k smallest distinct
+ * distance values `run` ([n][k], first != 0: starts it) and writes cutoff[x] = their largest
+ * (+inf while fewer than k are known).  Only valid where the merged row is sorted as a whole
+ * (k*tries a power of two >= 16; alg.c:139 prefix rule) — the caller decides.  k <= 16.
+ * Replaces nothing in the reference: it removes work whose result compute.cl:181-217 discards. */
+int annb_cutoff_applies(size_t d, size_t d_short, size_t k);
+void annb_leaf_cutoff_mode(int on);
+void annb_cutoff_update(const ftype *new_dist, ftype *run, ftype *cutoff, size_t n, size_t k, int first,
+                        annb_stream stream);
+void annb_leaf_topk_cut(const ftype *sorted_points, const ftype *mean, const annb_u32 *order,
+                        const annb_u32 *offset, const annb_u32 *hash, const annb_u32 *tmax, size_t n,
+                        size_t d, size_t d_short, size_t k, annb_u32 *list_ids, ftype *list_dist,
+                        void *scratch, int *status, const unsigned *scale_bits, int rows_prepared,
+                        const ftype *cutoff, annb_stream stream);
+
 /* Screened S3 path (float rows, d in {16, 32, 64}, k <= 16): fp16 tensor-core brackets of every
  * candidate distance decide which candidates go through the exact tree; the lists are the same
  * as the tiled kernel's, bit for bit.
