@@ -224,6 +224,8 @@ def gpu_backend(dtype) -> Backend:
     dt = np.dtype(dtype)
     if dt not in _loaded:
         path = os.path.join(_PKG, f"libann_b200_{_SUFFIX[dt]}.so")
+        # experiments only (tools/variants.py): a side build of the same library
+        path = os.environ.get(f"ANN_B200_LIB_{_SUFFIX[dt].upper()}") or path
         b = Backend(path, dt, "precomp_gpu", "query_gpu", "free_save")
         L = b.lib
         L.gpu_init.restype = None

@@ -232,8 +232,23 @@ __device__ __forceinline__ void count_less(u32 &less, float a, float b) {
   asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(less) : "f"(a), "f"(b));
 }
 
+// Build-time knobs of the kernel (tools/variants.py builds and times alternatives side by side;
+// cfg3, leaf stage per step: depth 3 / tables 0: 9.99 ms, 4 / 0: 9.95, 3 / 1: 9.82, 4 / 1: 9.77):
+//   SCR_DEPTH    candidate tiles of pass 1 in flight (3 or 4)
+//   SCR_TABLES4  1: the candidate tables are filled four stream positions per lane at a time (the
+//                norm loads of a bucket overlap) and the next bucket's ticket is drawn one bucket ahead
+//   SCR_REGCAP   register cap
+#ifndef SCR_DEPTH
+#define SCR_DEPTH 4
+#endif
+#ifndef SCR_TABLES4
+#define SCR_TABLES4 1
+#endif
+#ifndef SCR_REGCAP
+#define SCR_REGCAP 160
+#endif
 template <int D>
-__global__ void __maxnreg__(160)
+__global__ void __maxnreg__(SCR_REGCAP)
 leaf_screen_kernel(const float *__restrict__ sp, const unsigned short *__restrict__ sp16,
                    const float2 *__restrict__ nrm, const u32 *__restrict__ order,
                    const u32 *__restrict__ offset, const u32 *__restrict__ tmax_p, size_t n,
@@ -271,11 +286,21 @@ leaf_screen_kernel(const float *__restrict__ sp, const unsigned short *__restric
     if (sc >= 1.0f / 268435456.0f && sc <= 4294967296.0f) cut_scale2 = (double)sc * (double)sc;
   }
 
+#if SCR_TABLES4
+  u32 next_ticket = 0;
+  if (lane == 0) next_ticket = atomicAdd(ticket, 1u);
+#endif
   for (;;) {
     size_t b = 0;
+#if SCR_TABLES4
+    b = __shfl_sync(FULL, next_ticket, 0);
+    if (b >= buckets) return;
+    if (lane == 0) next_ticket = atomicAdd(ticket, 1u);               // waited for one bucket later
+#else
     if (lane == 0) b = atomicAdd(ticket, 1u);
     b = __shfl_sync(FULL, (u32)b, 0);
     if (b >= buckets) return;
+#endif
     const u32 beg = offset[b], Q = offset[b + 1] - beg;
     if (Q == 0) continue;
     const unsigned long long tmax = *tmax_p;
@@ -310,6 +335,35 @@ leaf_screen_kernel(const float *__restrict__ sp, const unsigned short *__restric
 
     if (!overflow) {
       int seg = 0;
+#if SCR_TABLES4
+      for (u32 j0 = lane; j0 < C16; j0 += 128) {
+        u32 rows[4];
+        float2 nr[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const u32 j = j0 + 32 * u;
+          rows[u] = beg;
+          if (j < C) {
+            while (j >= segpos[seg + 1]) seg++;
+            rows[u] = segrow[seg] + (j - segpos[seg]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          nr[u] = make_float2(0.f, inf);                               // tail of the last tile: D' = +inf
+          if (j0 + 32 * u < C) nr[u] = nrm[rows[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const u32 j = j0 + 32 * u;
+          if (j < C16) {
+            cand_row[j] = rows[u];
+            cand_s[j] = nr[u].x;
+            cand_n2[j] = nr[u].y;
+          }
+        }
+      }
+#else
       for (u32 j = lane; j < C16; j += 32) {
         u32 row = beg;
         float2 nr = make_float2(0.f, inf);                             // tail of the last tile: D' = +inf
@@ -322,6 +376,7 @@ leaf_screen_kernel(const float *__restrict__ sp, const unsigned short *__restric
         cand_s[j] = nr.x;
         cand_n2[j] = nr.y;
       }
+#endif
       __syncwarp();
     }
 
@@ -397,21 +452,32 @@ leaf_screen_kernel(const float *__restrict__ sp, const unsigned short *__restric
         // three candidate tiles in flight, buffers in fixed roles (no register rotation: a load
         // is only waited for three tiles after it was issued)
         const u32 C8 = (C + 7) & ~7u;
+        constexpr u32 STEP = 8 * SCR_DEPTH;
         ScreenRow<D> r0, r1, r2;
         r0.load(sp16 + (size_t)cand_row[g] * D, t);
         if (8 < C8) r1.load(sp16 + (size_t)cand_row[8 + g] * D, t);
         if (16 < C8) r2.load(sp16 + (size_t)cand_row[16 + g] * D, t);
-        for (u32 j0 = 0; j0 < C8; j0 += 24) {
+#if SCR_DEPTH == 4
+        ScreenRow<D> r3;
+        if (24 < C8) r3.load(sp16 + (size_t)cand_row[24 + g] * D, t);
+#endif
+        for (u32 j0 = 0; j0 < C8; j0 += STEP) {
           tile(r0, j0);
-          if (j0 + 24 < C8) r0.load(sp16 + (size_t)cand_row[j0 + 24 + g] * D, t);
+          if (j0 + STEP < C8) r0.load(sp16 + (size_t)cand_row[j0 + STEP + g] * D, t);
           if (j0 + 8 < C8) {
             tile(r1, j0 + 8);
-            if (j0 + 32 < C8) r1.load(sp16 + (size_t)cand_row[j0 + 32 + g] * D, t);
+            if (j0 + STEP + 8 < C8) r1.load(sp16 + (size_t)cand_row[j0 + STEP + 8 + g] * D, t);
           }
           if (j0 + 16 < C8) {
             tile(r2, j0 + 16);
-            if (j0 + 40 < C8) r2.load(sp16 + (size_t)cand_row[j0 + 40 + g] * D, t);
+            if (j0 + STEP + 16 < C8) r2.load(sp16 + (size_t)cand_row[j0 + STEP + 16 + g] * D, t);
           }
+#if SCR_DEPTH == 4
+          if (j0 + 24 < C8) {
+            tile(r3, j0 + 24);
+            if (j0 + STEP + 24 < C8) r3.load(sp16 + (size_t)cand_row[j0 + STEP + 24 + g] * D, t);
+          }
+#endif
         }
         if (C8 < C16) {                                                  // columns the scan reads beyond the last tile
           *reinterpret_cast<u32 *>(&lo_h[(size_t)g * CT + C8 + 2 * t]) = 0x7c007c00u;
