@@ -666,13 +666,17 @@ leaf_screen_kernel(const float *__restrict__ sp, const unsigned short *__restric
         }
       }
       __syncwarp();
-      if ((u32)lane < Qp) {
-        for (u32 i = qcnt[lane]; i < (u32)k; i++) {                     // fewer than k candidates in the row
-          list_ids[(size_t)qids[lane] * k + i] = sentinel;
-          list_dist[(size_t)qids[lane] * k + i] = inf;
+      // fewer than k survivors in a row (the rule with a cutoff): (n, +inf) behind them.  Slot
+      // (query e >> 4, position e & 15), so that a store instruction covers whole rows (k <= 16)
+      for (u32 e = lane; e < 256; e += 32) {
+        const u32 q = e >> 4, i = e & 15;
+        if (q < Qp && i < (u32)k && i >= qcnt[q]) {
+          const size_t o = (size_t)qids[q] * k + i;
+          list_ids[o] = sentinel;
+          list_dist[o] = inf;
         }
-        if (qtie[lane]) tie_report(ties, qids[lane]);
       }
+      if ((u32)lane < Qp && qtie[lane]) tie_report(ties, qids[lane]);
       __syncwarp();
     }
 
