@@ -61,6 +61,10 @@ static __thread struct {
   cudaEvent_t ev[2 * ANNH_MAX_SPANS];
   int span_stage[ANNH_MAX_SPANS];
   int spans;
+  /* second stream: the bucket tables and sorted copies of try j+1 are built while try j's lists
+   * are computed (precomp step 6); events order the two, buffers alternate                    */
+  cudaStream_t stream2;
+  cudaEvent_t ev_ready, ev_s2[2], ev_leaf[2];
 } G;
 
 static void gpu_init_device(int forced_device);
@@ -88,7 +92,13 @@ static void gpu_init_device(int forced_device) {
   CK(cudaSetDevice(dev));
   G.device = dev;
   CK(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&G.stream2, cudaStreamNonBlocking));
   for (int i = 0; i < 2 * ANNH_MAX_SPANS; i++) CK(cudaEventCreate(&G.ev[i]));
+  CK(cudaEventCreateWithFlags(&G.ev_ready, cudaEventDisableTiming));
+  for (int i = 0; i < 2; i++) {
+    CK(cudaEventCreateWithFlags(&G.ev_s2[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&G.ev_leaf[i], cudaEventDisableTiming));
+  }
   const char *tm = getenv("ANN_B200_TIMING");
   G.timing = tm && *tm && *tm != '0';
   G.ready = 1;
@@ -115,6 +125,7 @@ void annh_gpu_cleanup_impl(void) {
     free(h);
   }
   CK(cudaStreamSynchronize(G.stream));
+  CK(cudaStreamSynchronize(G.stream2));
   annh_egress_release();
   annh_ingest_release();
   if (G.table_buf) CK(cudaFree(G.table_buf));
@@ -124,6 +135,9 @@ void annh_gpu_cleanup_impl(void) {
   G.arena = NULL;
   G.arena_bytes = G.arena_used = 0;
   for (int i = 0; i < 2 * ANNH_MAX_SPANS; i++) CK(cudaEventDestroy(G.ev[i]));
+  CK(cudaEventDestroy(G.ev_ready));
+  for (int i = 0; i < 2; i++) { CK(cudaEventDestroy(G.ev_s2[i])); CK(cudaEventDestroy(G.ev_leaf[i])); }
+  CK(cudaStreamDestroy(G.stream2));
   CK(cudaStreamDestroy(G.stream));
   G.ready = 0;
 }
@@ -305,16 +319,18 @@ static void projection_rows(const host_transform *t, size_t rots_b, size_t len_b
 /* stage timing (CUDA events on the library stream; off unless asked for)                */
 
 /* a span = [begin, end) event pair on the library stream, attributed to one stage          */
-static int span_begin(int stage) {
+static int span_begin_on(int stage, cudaStream_t s) {
   if (!G.timing || G.spans >= ANNH_MAX_SPANS) return -1;
   int id = G.spans++;
   G.span_stage[id] = stage;
-  CK(cudaEventRecord(G.ev[2 * id], G.stream));
+  CK(cudaEventRecord(G.ev[2 * id], s));
   return id;
 }
-static void span_end(int id) {
-  if (id >= 0) CK(cudaEventRecord(G.ev[2 * id + 1], G.stream));
+static void span_end_on(int id, cudaStream_t s) {
+  if (id >= 0) CK(cudaEventRecord(G.ev[2 * id + 1], s));
 }
+static int span_begin(int stage) { return span_begin_on(stage, G.stream); }
+static void span_end(int id) { span_end_on(id, G.stream); }
 static void collect_times(void) {
   memset(&G.last, 0, sizeof G.last);
   if (!G.timing || G.spans == 0) { G.spans = 0; return; }
@@ -502,14 +518,29 @@ size_t *annh_precomp_impl(size_t n, size_t k, size_t d, const ftype *points, int
    * i.e. k*tries is a power of two (no prefix cut, no corner rule), and every list is merged at once */
   int use_cut = Tl >= 2 && k * T >= 16 && ((k * T) & (k * T - 1)) == 0 && annb_cutoff_applies(d, d_short, k);
   if (use_cut) fixed += pad256(n * k * w) + pad256(n * w);
-  size_t group = Tl ? Tl : 1;                                  /* lists kept before a merge */
-  if (!sharded && fixed + group * list_bytes + 512 > G.arena_bytes) {
-    /* the arena has to grow: see what the device can give (cudaMemGetInfo costs milliseconds,
-     * so it is not asked when the cached arena already fits the whole plan)                  */
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
-    free_b += G.arena_bytes;
-    while (group > 1 && fixed + group * list_bytes + 512 > free_b * 9 / 10) group--;
+  /* S2 of try j+1 on a second stream while S3 of try j runs (ANN_B200_PIPE=0 switches it off):
+   * a second set of the per-try buffers (offsets, order, sorted copy, leaf scratch)            */
+  int pipe = Tl >= 2;
+  {
+    const char *e = getenv("ANN_B200_PIPE");
+    if (e && *e && *e == '0') pipe = 0;
+  }
+  const size_t pipe_bytes = pad256(n * d * w) + pad256(scratch_bytes) + pad256((buckets + 1) * 4) + pad256(n * 4);
+  size_t group;                                                /* lists kept before a merge */
+  for (;;) {
+    const size_t fx = fixed + (pipe ? pipe_bytes : 0);
+    group = Tl ? Tl : 1;
+    if (!sharded && fx + group * list_bytes + 512 > G.arena_bytes) {
+      /* the arena has to grow: see what the device can give (cudaMemGetInfo costs milliseconds,
+       * so it is not asked when the cached arena already fits the whole plan)                  */
+      size_t free_b = 0, total_b = 0;
+      CK(cudaMemGetInfo(&free_b, &total_b));
+      free_b += G.arena_bytes;
+      while (group > 1 && fx + group * list_bytes + 512 > free_b * 9 / 10) group--;
+    }
+    if (pipe && group < Tl) { pipe = 0; continue; }            /* no room for the second set */
+    fixed = fx;
+    break;
   }
   {
     /* ANN_B200_MERGE_GROUP=g forces the grouped merge (tests; otherwise only a list set that does
@@ -531,7 +562,7 @@ size_t *annh_precomp_impl(size_t n, size_t k, size_t d, const ftype *points, int
       warned = 1;
     }
   }
-  if (group < Tl) use_cut = 0;
+  if (group < Tl) { use_cut = 0; pipe = 0; }
   annh_arena_reserve(fixed + group * list_bytes + 512);
 
   ftype *dX = annh_arena_take(np * d * w), *dXs = annh_arena_take(n * d * w), *dmean = annh_arena_take(d * w);
@@ -564,6 +595,11 @@ size_t *annh_precomp_impl(size_t n, size_t k, size_t d, const ftype *points, int
   void *dN16 = s5_screened ? annh_arena_take(n * 8) : NULL;
   void *dlocal = s5_local ? annh_arena_take(local_bytes) : NULL;
   annb_u32 *dperm = s5_local ? annh_arena_take(my_rows * 4) : NULL;
+  /* the per-try buffers, twice when S2 is pipelined against S3 (set j & 1 serves try j) */
+  ftype *Xs_set[2] = {dXs, pipe ? (ftype *)annh_arena_take(n * d * w) : dXs};
+  void *scratch_set[2] = {dscratch, pipe ? annh_arena_take(scratch_bytes) : dscratch};
+  annb_u32 *offset_set[2] = {doffset, pipe ? (annb_u32 *)annh_arena_take((buckets + 1) * 4) : doffset};
+  annb_u32 *order_set[2] = {dorder, pipe ? (annb_u32 *)annh_arena_take(n * 4) : dorder};
   ftype *drun = use_cut ? annh_arena_take(n * k * w) : NULL;    /* k smallest distinct distances so far */
   ftype *dcut = use_cut ? annh_arena_take(n * w) : NULL;        /* their largest: the cutoff of a point  */
   annb_u32 *dhash_all = (sharded && save) ? annh_arena_take(T * n * 4) : NULL;
@@ -651,27 +687,45 @@ size_t *annh_precomp_impl(size_t n, size_t k, size_t d, const ftype *points, int
   }
   int have_merged = 0;
   int admit[64];
+  cudaStream_t sb = pipe ? G.stream2 : st;                     /* where S2 runs */
+  if (pipe) {
+    CK(cudaEventRecord(G.ev_ready, st));                        /* hashes (and the save preliminaries) done */
+    CK(cudaStreamWaitEvent(sb, G.ev_ready, 0));
+  }
   for (size_t j0 = 0; j0 < Tl; j0 += group) {
     size_t g = Tl - j0 < group ? Tl - j0 : group;
     if (g > 64) annh_fatal("%s", "more than 64 tries per merge group");
     for (size_t j = 0; j < g; j++) {
       size_t t = own[j0 + j];
       const annb_u32 *hash_t = dhash + (j0 + j) * n;
-      sp = span_begin(3);
-      annb_build_buckets(hash_t, n, buckets, dcount, doffset, dorder_tmp, dorder, dtmax + t, dscan, st);
-      if (tb) {                                    /* padded table for save->which_par[t] */
-        annb_export_table32(doffset, dorder, n, buckets, h_tm_all[t], dtab[t], st);
-        annh_tables_submit(tb, (int)t, dtab[t], st);
+      /* S2 of try jj into buffer set jj & 1.  Unpipelined: try j, right here.  Pipelined (one group,
+       * j0 = 0): try 0 before the first S3, and try j + 1 now, so that it runs beside S3 of try j;
+       * its buffers were last read by S3 of try j - 1                                            */
+      for (size_t jj = (pipe && j > 0) ? j + 1 : j; jj <= (pipe ? j + 1 : j) && jj < g; jj++) {
+        const size_t tt = own[j0 + jj];
+        const int set = pipe ? (int)(jj & 1) : 0;
+        if (pipe && jj >= 2) CK(cudaStreamWaitEvent(sb, G.ev_leaf[set], 0));
+        sp = span_begin_on(3, sb);
+        annb_build_buckets(dhash + (j0 + jj) * n, n, buckets, dcount, offset_set[set], dorder_tmp, order_set[set],
+                           dtmax + tt, dscan, sb);
+        if (tb) {                                  /* padded table for save->which_par[t] */
+          annb_export_table32(offset_set[set], order_set[set], n, buckets, h_tm_all[tt], dtab[tt], sb);
+          annh_tables_submit(tb, (int)tt, dtab[tt], sb);
+        }
+        if (screened) annb_gather_rows_screen(dX, order_set[set], n, d, dmean, dscreen, Xs_set[set], scratch_set[set], sb);
+        else annb_gather_rows(dX, order_set[set], n, d, Xs_set[set], sb);
+        span_end_on(sp, sb);
+        if (pipe) CK(cudaEventRecord(G.ev_s2[set], sb));
       }
-      if (screened) annb_gather_rows_screen(dX, dorder, n, d, dmean, dscreen, dXs, dscratch, st);
-      else annb_gather_rows(dX, dorder, n, d, dXs, st);
-      span_end(sp);
+      const int set = pipe ? (int)(j & 1) : 0;
+      if (pipe) CK(cudaStreamWaitEvent(st, G.ev_s2[set], 0));
       sp = span_begin(4);
-      annb_leaf_topk_cut(dXs, dmean, dorder, doffset, hash_t, dtmax + t, n, d, d_short, k, dl_ids + j * n * k,
-                         dl_dist + j * n * k, dscratch, dstatus, screened ? dscreen : NULL, screened,
-                         (use_cut && j > 0) ? dcut : NULL, st);
+      annb_leaf_topk_cut(Xs_set[set], dmean, order_set[set], offset_set[set], hash_t, dtmax + t, n, d, d_short, k,
+                         dl_ids + j * n * k, dl_dist + j * n * k, scratch_set[set], dstatus,
+                         screened ? dscreen : NULL, screened, (use_cut && j > 0) ? dcut : NULL, st);
       if (use_cut && j + 1 < Tl) annb_cutoff_update(dl_dist + j * n * k, drun, dcut, n, k, j == 0, st);
       span_end(sp);
+      if (pipe) CK(cudaEventRecord(G.ev_leaf[set], st));
       admit[j] = annb200_dist_admit(k, tries, (int)t);
     }
     if (!sharded) {

@@ -367,7 +367,7 @@ def extra_config_run(gpu, name, world, rank, steps=3, warmup=1):
         dt, st = one(i)
         if i >= warmup:
             call.append(dt)
-            dev.append(sum(st[k_] for k_ in ("means", "hash", "buckets", "leaf", "exchange", "merge", "supercharge")))
+            dev.append(st["first_to_last_event"] - st["upload"])       # spans overlap (S2 beside S3): not their sum
             last = st
     bad = 0
     if kept:
@@ -550,8 +550,10 @@ def main():
 
     step(pts, keep_rows)
 
-    dev_keys = ("means", "hash", "buckets", "leaf", "exchange", "merge", "supercharge")
-    dev_ms = [sum(s[k_] for k_ in dev_keys) for s in stages]
+    # device time of a step: from the end of the upload to the end of the last S5 chunk, by CUDA
+    # events on the library's stream.  (Not the sum of the stage spans: the bucket tables of try
+    # j+1 are built on a second stream while try j's lists are computed, so spans overlap.)
+    dev_ms = [s["first_to_last_event"] - s["upload"] for s in stages]
     dev_total_s = sum(dev_ms) / 1e3
     if world > 1:
         import torch.distributed as dist

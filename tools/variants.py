@@ -1,7 +1,7 @@
 """Build-time variants of one kernel file, built here and timed side by side in ONE gpurun call.
 
     python tools/variants.py build  name1:"-DSCR_DEPTH=4" name2:"-DSCR_TABLES4=1" ...
-    python tools/variants.py run    [bench args]        # on the GPU box: one bench line per variant
+    python tools/variants.py run    [env:NAME=VALUE ...] [bench args]   # on the GPU box: one bench line per variant
 
 `build` recompiles annb_leaf.cu and annb_finish.cu with the extra flags and links them with the
 other objects of the regular float build into
@@ -45,15 +45,20 @@ def build(specs, sources=("annb_leaf.cu", "annb_finish.cu")):
 
 
 def run(args):
-    libs = [("default", None)] + [(os.path.basename(p)[len("libann_b200_f32_"):-3], p)
-                                  for p in sorted(glob.glob(os.path.join(VDIR, "libann_b200_f32_*.so")))]
+    """`env:NAME=VALUE` arguments add runs of the regular library under that environment variable."""
+    libs = [("default", None, None)] + [(os.path.basename(p)[len("libann_b200_f32_"):-3], p, None)
+                                        for p in sorted(glob.glob(os.path.join(VDIR, "libann_b200_f32_*.so")))]
+    libs += [(a[4:], None, a[4:]) for a in args if a.startswith("env:")]
+    args = [a for a in args if not a.startswith("env:")]
     base = [sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu-baseline", "--pair-queries", "0",
             "--recall-sample", "0", "--extra-config", "none"] + (args or ["--steps", "10", "--warmup", "3"])
     for rep in range(2):
-        for name, path in libs:
+        for name, path, setenv in libs:
             env = dict(os.environ)
             if path:
                 env["ANN_B200_LIB_F32"] = path
+            if setenv:
+                env[setenv.split("=", 1)[0]] = setenv.split("=", 1)[1]
             r = subprocess.run(base, env=env, capture_output=True, text=True)
             try:
                 d = json.loads(r.stdout.strip().splitlines()[-1])
