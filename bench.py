@@ -655,7 +655,12 @@ def main():
                     "ms_per_step_with_stage_events": 1e3 * wall_instrumented / args.steps,
                     "pinned": {"value": n * args.steps / wall_pinned, "ms_per_step": 1e3 * wall_pinned / args.steps,
                                "input": "page-locked host array"}},
-            "gpu_launches": launches, "stage_ms": mean_stage, "roofline": roofline, "roofline_hbm": roofline_hbm,
+            "gpu_launches": launches, "stage_ms": mean_stage,
+            "stage_ms_note": "CUDA-event spans per stage, summed over a step. With two or more owned tries the bucket "
+                             "tables of try j+1 (buckets) are built on a second stream beside the lists of try j "
+                             "(leaf): those spans overlap and stretch, and ms_per_step = first_to_last_event - upload "
+                             "is less than their sum (ANN_B200_PIPE=0 serialises them).",
+            "roofline": roofline, "roofline_hbm": roofline_hbm,
             "roofline_step": roofline_step, "clocks": sampler.summary(), "host_cores": os.cpu_count()}
     if world > 1:
         line["stage_ms_per_rank"] = stage_all
@@ -664,7 +669,21 @@ def main():
     if args.recall_sample > 0 and world == 1:
         line["recall"] = measure_recall(gpu, pts, cfg, args.recall_sample)
     if args.pair_queries > 0 and world == 1:
-        line["precomp_query_pair"] = measure_pair(gpu, pts, cfg, args.pair_queries)
+        line["precomp_query_pair"] = pq_ = measure_pair(gpu, pts, cfg, args.pair_queries)
+        # Q path against the HBM roof: the reference measures every real candidate of a query's
+        # tries*(d_short+1) table rows (alg.c:464-508), about tries*(d_short+1)*n/2^d_short rows of
+        # d*w bytes, then the k*k supercharge candidates.  Whole call, host buffers in and out.
+        d_short_ = int(np.ceil(np.log2(np.float32(n) / np.float32(k))))
+        cand_ = tries * (d_short_ + 1) * n / float(1 << d_short_)
+        bytes_ = args.pair_queries * ((cand_ + k * k) * (4 + d * w) + 2 * k * (4 + w))
+        ach_ = bytes_ / (pq_["query_resident_index_ms"] * 1e-3) / 1e9
+        line["roofline_query"] = {"kernel": "query_gpu on the resident index: query_hash_warp_kernel + query_rows_fast_kernel "
+                                            "+ supercharge (whole call, host buffers in and out)",
+                                  "bound": "hbm", "achieved": ach_, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                                  "frac": ach_ / peak, "traffic": None,
+                                  "algorithmic_candidates_per_query": cand_ + k * k,
+                                  "note": "algorithmic bytes of the reference's query (every candidate row read once); "
+                                          "the fp16 screen moves about half of them"}
     if run_baseline:
         want, line["cpu_baseline"] = cpu_baseline(cfg, pts, args.cpu_sample)
     else:
