@@ -680,7 +680,9 @@ def main():
         line["roofline_query"] = {"kernel": "query_gpu on the resident index: query_hash_warp_kernel + query_rows_fast_kernel "
                                             "+ supercharge (whole call, host buffers in and out)",
                                   "bound": "hbm", "achieved": ach_, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                                  "frac": ach_ / peak, "traffic": None,
+                                  "frac": ach_ / peak,
+                                  "traffic": committed_traffic(args.config, world).get("query_rows_fast_kernel")
+                                  if args.pair_queries == 65536 else None,
                                   "algorithmic_candidates_per_query": cand_ + k * k,
                                   "note": "algorithmic bytes of the reference's query (every candidate row read once); "
                                           "the fp16 screen moves about half of them"}
