@@ -147,3 +147,104 @@ def test_keeping_four_per_lane_and_parity_bounds_the_sixteenth_smallest():
         theta = _quad_sixteenth_smallest(lists)
         truth = np.sort(np.concatenate([hi, np.full(16, np.inf, np.float32)]))[15]
         assert theta >= truth
+
+
+# ---- cutoff carried from try to try: the comparison the scan makes -----------------------------
+
+def _half_round_toward_zero(v):
+    """cvt.rz.relu.f16.f32 of annb_leaf_screen.cuh (pack_lower_bounds): negatives -> 0, magnitude
+    rounded towards zero, +inf stays +inf."""
+    v = np.maximum(np.asarray(v, dtype=np.float64), 0.0)
+    h = v.astype(np.float16)                               # round to nearest
+    up = h.astype(np.float64) > v                          # rounded up: step one value down
+    h = np.where(up, np.nextafter(h, np.float16(0)), h).astype(np.float16)
+    return h
+
+
+def _half_round_up(v):
+    """__float2half_ru, with the kernel's clamp of +inf to the largest finite half."""
+    v = np.asarray(v, dtype=np.float64)
+    h = v.astype(np.float16)
+    down = h.astype(np.float64) < v
+    h = np.where(down, np.nextafter(h, np.float16(np.inf)), h).astype(np.float16)
+    return np.where(np.isinf(h), np.float16(65504.0), h)
+
+
+@pytest.mark.parametrize("d", [16, 64])
+def test_a_candidate_at_or_below_the_cutoff_always_passes_the_scan(d):
+    """annb_leaf_screen.cuh keeps a candidate when fp16_rz(lo) <= fp16_ru(float_ru(cutoff * scale^2)),
+    lo = D' - t^2.  The worst case for the rule is a cutoff EQUAL to the candidate's own exact
+    distance (it then is the point's current k-th neighbour and must stay in the list)."""
+    rng = np.random.default_rng(4321 + d)
+    n = 3000
+    for name, x in datasets(rng, n, d):
+        pairs = rng.integers(0, n, size=(100000, 2))
+        pairs = pairs[pairs[:, 0] != pairs[:, 1]]
+        dprime, slack, exact_scaled = brackets(x, pairs)
+        lo = _half_round_toward_zero(dprime - slack).astype(np.float64)
+        # the kernel scales the fp32 cutoff by scale^2 in double and rounds up twice; `exact_scaled`
+        # is that product for a cutoff equal to the pair's distance
+        thr = _half_round_up(np.nextafter(exact_scaled.astype(np.float32), np.float32(np.inf))).astype(np.float64)
+        assert np.all(lo <= thr), (name, float((lo - thr).max()))
+        # and a slightly larger cutoff (any later, looser bound) passes a fortiori
+        thr2 = _half_round_up(exact_scaled * 1.5 + 1e-3).astype(np.float64)
+        assert np.all(lo <= thr2), name
+
+
+def _cutoff_update_model(run, new, k, K=16):
+    """Line-by-line numpy model of cutoff_update_kernel<16> for one point: duplicate flags, bitonic
+    sort of the new list, reverse / min / bitonic merge with the running one."""
+    inf = np.float32(np.inf)
+    v = np.full(K, inf, np.float32); v[:k] = new
+    r = np.full(K, inf, np.float32); r[:k] = run
+    bad = bool(np.isnan(v).any() or np.isnan(r).any())
+    dup = np.zeros(K, bool)
+    for j in range(1, K):
+        dup[j] = v[j] == v[j - 1]
+    for j in range(K):
+        dup[j] |= bool((v[j] == r).any())
+    v[dup] = inf
+
+    def ce(a, i, p):
+        if a[p] < a[i]:
+            a[i], a[p] = a[p], a[i]
+    size = 2
+    while size <= K:
+        stride = size >> 1
+        while stride >= 1:
+            for i in range(K):
+                p = i ^ stride
+                if p > i:
+                    if (i & size) == 0:
+                        ce(v, i, p)
+                    else:
+                        ce(v, p, i)
+            stride >>= 1
+        size <<= 1
+    r = np.minimum(r, v[::-1])
+    stride = K >> 1
+    while stride >= 1:
+        for i in range(K):
+            p = i ^ stride
+            if p > i:
+                ce(r, i, p)
+        stride >>= 1
+    if bad:
+        r[:] = inf
+    return r[:k].copy(), r[k - 1]
+
+
+@pytest.mark.parametrize("k", [16, 10, 3])
+def test_cutoff_update_network_keeps_the_k_smallest_distinct_values(k):
+    rng = np.random.default_rng(100 + k)
+    for trial in range(400):
+        pool = rng.random(24).astype(np.float32)
+        run = np.full(k, np.inf, np.float32)
+        for step in range(5):
+            m = int(rng.integers(0, k + 1))
+            new = np.full(k, np.inf, np.float32)
+            new[:m] = np.sort(rng.choice(pool, size=m, replace=True))
+            want = np.unique(np.concatenate([run[np.isfinite(run)], new[np.isfinite(new)]]))[:k]
+            run, cutoff = _cutoff_update_model(run, new, k)
+            assert np.array_equal(run[: len(want)], want) and np.all(np.isinf(run[len(want):]))
+            assert cutoff == (want[k - 1] if len(want) >= k else np.inf)
